@@ -1,0 +1,121 @@
+/*
+ * pyrayhf_b200 -- C ABI of the B200-native vertical forward operator.
+ *
+ * The reference (victoriyaforsythe/PyRayHF v0.1.0) is pure Python and has no FFI; the seam it
+ * offers for this path is the module-level function
+ *     PyRayHF.library.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n_points)
+ * (PyRayHF/library.py:459-509, called by model_VH at library.py:589-591).  The entry points
+ * below are what a ctypes binding of that function binds; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns a prhf status code (0 = ok) and
+ *     never throws.  prhf_error_string() describes a code.
+ *   - units as the reference docstring (library.py:463-478): MHz, m^-3, Tesla, degrees, km.
+ *   - mode: 0 = 'O', 1 = 'X' (library.py:391-396).
+ *   - a prhf_ctx belongs to one CUDA device and caches the stretched-grid multiplier tables
+ *     (one per n_points) plus a small workspace.  Calls on one ctx must be issued from one
+ *     host thread / one stream at a time; create one ctx per stream for concurrency.
+ *   - per-profile status (int32): 0 ok; 1 negative density below the peak (the reference raises
+ *     ValueError, library.py:93-94); 2 density peak at index 0 (the reference raises IndexError at
+ *     library.py:399).  Rows of a failed profile are NaN.
+ */
+#ifndef PYRAYHF_B200_H
+#define PYRAYHF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRHF_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define PRHF_OK 0
+#define PRHF_ERR_INVALID_ARG 1    /* null pointer, negative size, n_points < 1 ...            */
+#define PRHF_ERR_BAD_MODE 2       /* mode not 0/1: ValueError("mode must be 'O' or 'X'")      */
+#define PRHF_ERR_CUDA 3           /* a CUDA runtime call failed; see prhf_last_cuda_error()   */
+#define PRHF_ERR_NALT_TOO_LARGE 4 /* n_alt exceeds the shared-memory staging limit            */
+#define PRHF_ERR_NO_DEVICE 5      /* no CUDA device / device is not sm_100                    */
+
+/* flags */
+#define PRHF_FLAG_DEFAULT 0u
+#define PRHF_FLAG_LITERAL 1u /* evaluate library.py:209-254 operation by operation (IEEE div/sqrt, \
+                                libdevice sincos) instead of the restructured fast form */
+
+/* per-profile status values */
+#define PRHF_PROFILE_OK 0
+#define PRHF_PROFILE_NEGATIVE_DENSITY 1
+#define PRHF_PROFILE_PEAK_AT_BOTTOM 2
+
+typedef struct prhf_ctx prhf_ctx;
+
+int prhf_version(void);
+const char* prhf_error_string(int code);
+/* cudaError_t of the last failing runtime call on this ctx (0 if none) and its text. */
+int prhf_last_cuda_error(const prhf_ctx* ctx, const char** text);
+
+/* device < 0: the current device. */
+int prhf_ctx_create(int device, prhf_ctx** out);
+void prhf_ctx_destroy(prhf_ctx* ctx);
+
+/* Largest n_alt the staging layout supports on this device. */
+int prhf_max_n_alt(const prhf_ctx* ctx);
+
+/*
+ * Stretched-grid multiplier m[n_points] in [0,1] (replaces smooth_nonuniform_grid(0, 1, n, 10.),
+ * library.py:296-321 as called from library.py:361-364).  m_out is a DEVICE pointer.
+ * Asynchronous on cuda_stream.
+ */
+int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* cuda_stream);
+
+/*
+ * Batched vertical forward operator on DEVICE buffers (replaces library.py:459-509 for every
+ * profile of the batch; row p of vh_out equals the reference called on profile p alone).
+ *
+ *   freq_mhz  [n_freq] when freq_profile_stride == 0, else profile p reads freq_mhz + p*stride
+ *   den, bmag, bpsi  [n_profiles x n_alt] row-major
+ *   alt       [n_alt] when alt_profile_stride == 0, else profile p reads alt + p*stride
+ *   vh_out    [n_profiles x n_freq] row-major, km, NaN where the ray does not reflect
+ *   status    [n_profiles] int32 (may be NULL)
+ *
+ * Asynchronous on cuda_stream; no host synchronisation.  All pointers are device pointers owned
+ * by the caller.
+ */
+int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
+                 const double* den, const double* bmag, const double* bpsi, const double* alt,
+                 int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode, int n_points,
+                 unsigned flags, double* vh_out, int* status, void* cuda_stream);
+
+/*
+ * Same operator on HOST buffers: stages the inputs through pinned memory, copies them to the
+ * device, runs prhf_vfo_f64 and copies vh/status back; returns after the results are in
+ * vh_out / status.  This is the call the Python drop-in makes for numpy inputs.
+ */
+int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
+                      const double* den, const double* bmag, const double* bpsi, const double* alt,
+                      int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode,
+                      int n_points, unsigned flags, double* vh_out, int* status);
+
+/*
+ * Elementwise phase / group refractive index on DEVICE buffers (replaces find_mu_mup,
+ * library.py:161-256, magnetised branch or isotropic branch chosen by the caller through
+ * `isotropic`, because the reference decides it from the whole array, library.py:201).
+ * mu_out / mup_out may be NULL.
+ */
+int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const double* bpsi_deg, int64_t n,
+                    int mode, int isotropic, unsigned flags, double* mu_out, double* mup_out,
+                    void* cuda_stream);
+
+/* Device FP64 FMA throughput probe used for the roofline denominator: runs a dependent-free DFMA
+ * kernel and returns the measured TFLOP/s (2 flop per FMA). */
+int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out);
+
+/* Number of kernel launches issued through this ctx since creation (for bench accounting). */
+int64_t prhf_launch_count(const prhf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRAYHF_B200_H */

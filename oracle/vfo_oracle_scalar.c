@@ -69,8 +69,8 @@ static int np_bracket(double x, const double *xp, int n) {
 
 /* numpy arr_interp for one query (left=fp[0], right=fp[n-1]) */
 static double np_interp1(double x, const double *xp, const double *fp, int n) {
+  if (n == 1) return fp[0];   /* numpy's lenxp == 1 branch has no NaN test: interp(NaN) -> fp[0] */
   if (isnan(x)) return x;
-  if (n == 1) return fp[0];
   int j = np_bracket(x, xp, n);
   if (j == -1) return fp[0];
   if (j == n) return fp[n - 1];

@@ -1,0 +1,22 @@
+"""pyrayhf_b200 -- B200-native (sm_100a) vertical forward operator for PyRayHF.
+
+Drop-in for ``PyRayHF.library.vertical_forward_operator`` (PyRayHF/library.py:459-509)
+plus a batched ``[n_profiles x n_alt]`` form.  The compute path is hand-written CUDA
+behind a C ABI (``include/pyrayhf_b200.h``); there is no CPU fallback.
+"""
+import logging
+
+# Same logger name as the reference package (PyRayHF/__init__.py:4-6) so that
+# applications capturing 'PyRayHF_logger' keep seeing the shape-mismatch message.
+logger = logging.getLogger('PyRayHF_logger')
+
+__version__ = "0.1.0"
+
+from pyrayhf_b200 import library  # noqa: E402,F401
+from pyrayhf_b200.library import (  # noqa: E402,F401
+    vertical_forward_operator,
+    vertical_forward_operator_batched,
+    find_mu_mup,
+    install,
+    uninstall,
+)

@@ -1,0 +1,394 @@
+// C ABI of pyrayhf_b200 (declared in include/pyrayhf_b200.h).
+//
+// Replaces the reference's Python entry point PyRayHF.library.vertical_forward_operator
+// (PyRayHF/library.py:459-509).  Host-side responsibilities kept here: argument validation with the
+// reference's error behaviour (library.py:396 bad mode), caching of the stretched-grid multiplier
+// table per n_points (library.py:361-364 recomputes it on every call), tile sizing, and the
+// pinned-memory staging of the host-buffer entry point.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <new>
+
+#include "../../include/pyrayhf_b200.h"
+#include "vfo_kernels.h"
+
+struct prhf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  std::mutex mu;
+  std::map<int, double*> mult;       // n_points -> device table
+  // workspace for split rows (partials + self-resetting counters)
+  double* partial = nullptr;
+  unsigned* counter = nullptr;
+  size_t partial_cap = 0, counter_cap = 0;
+  // host entry: device arena + pinned mirror + private stream
+  cudaStream_t stream = nullptr;
+  char* d_arena = nullptr;
+  char* h_arena = nullptr;
+  size_t arena_cap = 0;
+  int last_cuda_error = 0;
+  int64_t launches = 0;
+  int seg_len_override = 0;          // PRHF_SEG_LEN (tuning / tests)
+  int64_t target_tiles = 0;          // PRHF_TARGET_TILES
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+int fail(prhf_ctx* ctx, cudaError_t e) {
+  if (ctx) ctx->last_cuda_error = (int)e;
+  cudaGetLastError();  // clear sticky-less errors
+  return PRHF_ERR_CUDA;
+}
+
+#define PRHF_CUDA(ctx, call)                         \
+  do {                                               \
+    cudaError_t _e = (call);                         \
+    if (_e != cudaSuccess) return fail((ctx), _e);   \
+  } while (0)
+
+int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const double** out) {
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto it = ctx->mult.find(n_points);
+  if (it != ctx->mult.end()) {
+    *out = it->second;
+    return PRHF_OK;
+  }
+  double* m = nullptr;
+  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * (size_t)n_points));
+  cudaError_t e = prhf::launch_grid_multiplier(n_points, m, stream);
+  ctx->launches++;
+  if (e != cudaSuccess) {
+    cudaFree(m);
+    return fail(ctx, e);
+  }
+  // Make the table visible to every later stream: the cache outlives this call.
+  PRHF_CUDA(ctx, cudaStreamSynchronize(stream));
+  ctx->mult[n_points] = m;
+  *out = m;
+  return PRHF_OK;
+}
+
+int ensure_workspace(prhf_ctx* ctx, size_t n_partial, size_t n_counter) {
+  if (n_partial > ctx->partial_cap) {
+    if (ctx->partial) cudaFree(ctx->partial);
+    ctx->partial = nullptr;
+    ctx->partial_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->partial, sizeof(double) * n_partial));
+    ctx->partial_cap = n_partial;
+  }
+  if (n_counter > ctx->counter_cap) {
+    // A larger counter array replaces the old one; in-flight launches on the old array must finish.
+    PRHF_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->counter) cudaFree(ctx->counter);
+    ctx->counter = nullptr;
+    ctx->counter_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->counter, sizeof(unsigned) * n_counter));
+    PRHF_CUDA(ctx, cudaMemset(ctx->counter, 0, sizeof(unsigned) * n_counter));
+    ctx->counter_cap = n_counter;
+  }
+  return PRHF_OK;
+}
+
+// Tile sizing: split each (profile, frequency) row into n_seg segments so that a launch has enough
+// CTAs to fill 148 SMs several times over, but never below 1024 grid points per tile (per-tile setup
+// -- profile staging and the critical-curve scan -- is amortised over the tile's points).
+void choose_tiling(const prhf_ctx* ctx, int64_t rows, int n_points, int* seg_len, int* n_seg) {
+  if (ctx->seg_len_override > 0) {
+    int sl = std::min(ctx->seg_len_override, std::max(n_points, 1));
+    *seg_len = sl;
+    *n_seg = (n_points + sl - 1) / sl;
+    return;
+  }
+  const int64_t target = ctx->target_tiles > 0 ? ctx->target_tiles : (int64_t)ctx->sm_count * 16;
+  int64_t want = (target + rows - 1) / std::max<int64_t>(rows, 1);
+  const int max_seg = std::max(1, n_points / 1024);
+  want = std::max<int64_t>(1, std::min<int64_t>(want, max_seg));
+  int sl = (int)((n_points + want - 1) / want);
+  sl = ((sl + prhf::kThreads - 1) / prhf::kThreads) * prhf::kThreads;
+  sl = std::max(sl, 1);
+  *seg_len = sl;
+  *n_seg = (n_points + sl - 1) / sl;
+}
+
+int validate(const prhf_ctx* ctx, const void* freq, int n_freq, const void* den, const void* bmag, const void* bpsi,
+             const void* alt, int64_t n_profiles, int n_alt, int mode, int n_points, const void* vh) {
+  if (!ctx) return PRHF_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return PRHF_ERR_BAD_MODE;
+  if (n_freq < 0 || n_profiles < 0 || n_alt < 1 || n_points < 1) return PRHF_ERR_INVALID_ARG;
+  if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
+  if (!freq || !den || !bmag || !bpsi || !alt || !vh) return PRHF_ERR_INVALID_ARG;
+  if (prhf::vfo_smem_bytes(n_alt) > (size_t)ctx->max_smem_optin) return PRHF_ERR_NALT_TOO_LARGE;
+  return PRHF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int prhf_version(void) { return PRHF_VERSION; }
+
+const char* prhf_error_string(int code) {
+  switch (code) {
+    case PRHF_OK: return "ok";
+    case PRHF_ERR_INVALID_ARG: return "invalid argument";
+    case PRHF_ERR_BAD_MODE: return "mode must be 'O' or 'X'";
+    case PRHF_ERR_CUDA: return "CUDA runtime error";
+    case PRHF_ERR_NALT_TOO_LARGE: return "n_alt exceeds the shared-memory staging limit";
+    case PRHF_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required)";
+    default: return "unknown error";
+  }
+}
+
+int prhf_last_cuda_error(const prhf_ctx* ctx, const char** text) {
+  const int e = ctx ? ctx->last_cuda_error : 0;
+  if (text) *text = cudaGetErrorString((cudaError_t)e);
+  return e;
+}
+
+int prhf_ctx_create(int device, prhf_ctx** out) {
+  if (!out) return PRHF_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return PRHF_ERR_NO_DEVICE;
+  }
+  if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return PRHF_ERR_NO_DEVICE;
+  if (device >= count) return PRHF_ERR_INVALID_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PRHF_ERR_NO_DEVICE;
+  if (prop.major != 10) return PRHF_ERR_NO_DEVICE;   // the only code object in this library is sm_100a
+  prhf_ctx* ctx = new (std::nothrow) prhf_ctx();
+  if (!ctx) return PRHF_ERR_INVALID_ARG;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
+  if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
+  DeviceGuard g(device);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return PRHF_ERR_CUDA;
+  }
+  *out = ctx;
+  return PRHF_OK;
+}
+
+void prhf_ctx_destroy(prhf_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->mult) cudaFree(kv.second);
+  if (ctx->partial) cudaFree(ctx->partial);
+  if (ctx->counter) cudaFree(ctx->counter);
+  if (ctx->d_arena) cudaFree(ctx->d_arena);
+  if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int prhf_max_n_alt(const prhf_ctx* ctx) {
+  if (!ctx) return 0;
+  return (int)((size_t)ctx->max_smem_optin / prhf::vfo_smem_bytes(1));
+}
+
+int64_t prhf_launch_count(const prhf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* cuda_stream) {
+  if (!ctx || n_points < 1 || !m_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_grid_multiplier(n_points, m_out, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride, const double* den,
+                 const double* bmag, const double* bpsi, const double* alt, int64_t alt_profile_stride,
+                 int64_t n_profiles, int n_alt, int mode, int n_points, unsigned flags, double* vh_out, int* status,
+                 void* cuda_stream) {
+  int rc = validate(ctx, freq_mhz, n_freq, den, bmag, bpsi, alt, n_profiles, n_alt, mode, n_points, vh_out);
+  if (rc != PRHF_OK) return rc;
+  if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const double* mult = nullptr;
+  rc = get_multiplier(ctx, n_points, stream, &mult);
+  if (rc != PRHF_OK) return rc;
+
+  const int64_t rows_total = n_profiles * (int64_t)n_freq;
+  int seg_len = 0, n_seg = 0;
+  choose_tiling(ctx, rows_total, n_points, &seg_len, &n_seg);
+
+  // A launch covers at most max_tiles tiles (grid.x limit); profiles are chunked accordingly.
+  const int64_t max_tiles = (int64_t)1 << 30;
+  const int64_t tiles_per_profile = (int64_t)n_freq * n_seg;
+  if (tiles_per_profile > max_tiles) return PRHF_ERR_INVALID_ARG;
+  const int64_t prof_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_profile);
+  if (n_seg > 1) {
+    const int64_t rows_launch = std::min(prof_per_launch, n_profiles) * n_freq;
+    rc = ensure_workspace(ctx, (size_t)rows_launch * n_seg, (size_t)rows_launch);
+    if (rc != PRHF_OK) return rc;
+  }
+  for (int64_t p0 = 0; p0 < n_profiles; p0 += prof_per_launch) {
+    const int64_t np = std::min(prof_per_launch, n_profiles - p0);
+    prhf::VfoParams P;
+    P.freq = freq_mhz;
+    P.freq_stride = freq_profile_stride;
+    P.n_freq = n_freq;
+    P.den = den;
+    P.bmag = bmag;
+    P.bpsi = bpsi;
+    P.alt = alt;
+    P.alt_stride = alt_profile_stride;
+    P.n_alt = n_alt;
+    P.profile_offset = p0;
+    P.mult = mult;
+    P.n_points = n_points;
+    P.seg_len = seg_len;
+    P.n_seg = n_seg;
+    P.vh = vh_out;
+    P.status = status;
+    P.partial = ctx->partial;
+    P.counter = ctx->counter;
+    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, (flags & PRHF_FLAG_LITERAL) != 0, np * tiles_per_profile, stream));
+    ctx->launches++;
+  }
+  return PRHF_OK;
+}
+
+int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
+                      const double* den, const double* bmag, const double* bpsi, const double* alt,
+                      int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode, int n_points,
+                      unsigned flags, double* vh_out, int* status) {
+  int rc = validate(ctx, freq_mhz, n_freq, den, bmag, bpsi, alt, n_profiles, n_alt, mode, n_points, vh_out);
+  if (rc != PRHF_OK) return rc;
+  if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
+  DeviceGuard g(ctx->device);
+
+  // Profiles are processed in chunks through one packed arena:
+  //   inputs  [freq | alt | den | bmag | bpsi]   (one H2D copy per chunk)
+  //   outputs [vh | status]                      (one D2H copy per chunk)
+  const size_t d8 = sizeof(double);
+  const bool freq_shared = (freq_profile_stride == 0), alt_shared = (alt_profile_stride == 0);
+  const size_t per_prof_in = d8 * ((freq_shared ? 0 : (size_t)n_freq) + (alt_shared ? 0 : (size_t)n_alt) + 3 * (size_t)n_alt);
+  const size_t per_prof_out = d8 * (size_t)n_freq + sizeof(int);
+  const size_t shared_in = d8 * ((freq_shared ? (size_t)n_freq : 0) + (alt_shared ? (size_t)n_alt : 0));
+  const size_t budget = (size_t)256 << 20;
+  int64_t chunk = (int64_t)std::max<size_t>(1, (budget - std::min(budget / 2, shared_in)) / (per_prof_in + per_prof_out));
+  chunk = std::min<int64_t>(chunk, n_profiles);
+  const size_t in_bytes = shared_in + per_prof_in * (size_t)chunk;
+  const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+  const size_t vh_bytes = d8 * (size_t)n_freq * (size_t)chunk;
+  const size_t need = out_off + vh_bytes + sizeof(int) * (size_t)chunk + 256;
+  if (need > ctx->arena_cap) {
+    PRHF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+    ctx->d_arena = ctx->h_arena = nullptr;
+    ctx->arena_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->d_arena, need));
+    PRHF_CUDA(ctx, cudaMallocHost(&ctx->h_arena, need));
+    ctx->arena_cap = need;
+  }
+  for (int64_t p0 = 0; p0 < n_profiles; p0 += chunk) {
+    const int64_t np = std::min(chunk, n_profiles - p0);
+    size_t off = 0;
+    // copy `rows` rows of `count` doubles (source row stride `stride` doubles) densely into the arena
+    auto put = [&](const double* src, int64_t stride, size_t count, int64_t rows) {
+      const size_t at = off;
+      if (rows == 1 || stride == (int64_t)count) {
+        memcpy(ctx->h_arena + off, src, d8 * count * (size_t)rows);
+      } else {
+        for (int64_t q = 0; q < rows; ++q) memcpy(ctx->h_arena + off + d8 * count * (size_t)q, src + q * stride, d8 * count);
+      }
+      off += d8 * count * (size_t)rows;
+      return at;
+    };
+    const size_t o_freq = freq_shared ? put(freq_mhz, 0, (size_t)n_freq, 1)
+                                      : put(freq_mhz + p0 * freq_profile_stride, freq_profile_stride, (size_t)n_freq, np);
+    const size_t o_alt = alt_shared ? put(alt, 0, (size_t)n_alt, 1)
+                                    : put(alt + p0 * alt_profile_stride, alt_profile_stride, (size_t)n_alt, np);
+    const size_t o_den = put(den + p0 * n_alt, n_alt, (size_t)n_alt, np);
+    const size_t o_b = put(bmag + p0 * n_alt, n_alt, (size_t)n_alt, np);
+    const size_t o_psi = put(bpsi + p0 * n_alt, n_alt, (size_t)n_alt, np);
+    PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, off, cudaMemcpyHostToDevice, ctx->stream));
+    double* d_vh = (double*)(ctx->d_arena + out_off);
+    int* d_st = (int*)(ctx->d_arena + out_off + d8 * (size_t)n_freq * np);
+    rc = prhf_vfo_f64(ctx, (const double*)(ctx->d_arena + o_freq), n_freq, freq_shared ? 0 : n_freq,
+                      (const double*)(ctx->d_arena + o_den), (const double*)(ctx->d_arena + o_b),
+                      (const double*)(ctx->d_arena + o_psi), (const double*)(ctx->d_arena + o_alt),
+                      alt_shared ? 0 : n_alt, np, n_alt, mode, n_points, flags, d_vh, d_st, ctx->stream);
+    if (rc != PRHF_OK) return rc;
+    const size_t out_bytes = d8 * (size_t)n_freq * np + sizeof(int) * (size_t)np;
+    PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->h_arena + out_off, ctx->d_arena + out_off, out_bytes, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+    PRHF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(vh_out + p0 * n_freq, ctx->h_arena + out_off, d8 * (size_t)n_freq * np);
+    if (status) memcpy(status + p0, ctx->h_arena + out_off + d8 * (size_t)n_freq * np, sizeof(int) * (size_t)np);
+  }
+  return PRHF_OK;
+}
+
+int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const double* bpsi_deg, int64_t n, int mode,
+                    int isotropic, unsigned flags, double* mu_out, double* mup_out, void* cuda_stream) {
+  if (!ctx || n < 0) return PRHF_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return PRHF_ERR_BAD_MODE;
+  if (n == 0) return PRHF_OK;
+  if (!X || (!isotropic && (!Y || !bpsi_deg))) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_mu_mup(X, Y, bpsi_deg, n, mode, isotropic != 0, (flags & PRHF_FLAG_LITERAL) != 0, mu_out,
+                                     mup_out, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  double* d = nullptr;
+  PRHF_CUDA(ctx, cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  PRHF_CUDA(ctx, cudaEventCreate(&e0));
+  PRHF_CUDA(ctx, cudaEventCreate(&e1));
+  const int blocks = ctx->sm_count * 8, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    cudaError_t e = prhf::launch_dfma_probe(d, blocks, iters, ctx->stream);
+    ctx->launches++;
+    cudaEventRecord(e1, ctx->stream);
+    if (e != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) {
+      cudaFree(d);
+      return fail(ctx, e != cudaSuccess ? e : cudaGetLastError());
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
+  return PRHF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Device-side math of the vertical forward operator (sm_100a, FP64).
+//
+// Reference behaviour being replaced (PyRayHF/library.py, "lib"):
+//   lib:120-158  find_X / find_Y            -> x_literal / y_literal and the per-row scale factors
+//   lib:161-256  find_mu_mup                -> ah_literal (operation by operation) and ah_fast
+//   lib:424-426  np.interp of den/bmag/bpsi -> interp_numpy (numpy arr_interp semantics) / fma form
+//
+// Tensor cores are not used: the path is ~90 dependent FP64 scalar operations per grid point with
+// no contraction structure; it is bounded by the FP64 pipe (DESIGN.md "Roofline").
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace prhf {
+
+constexpr double kCp = 8.97866275;          // lib:61
+constexpr double kGp = 2.799249247e10;      // lib:64
+constexpr double kSharp = 10.0;             // lib:363
+constexpr double kBackoff = 1e-6;           // lib:378 (the dh argument is overwritten)
+constexpr double kYTol = 1e-12;             // lib:163
+constexpr double kDeg2Rad = 0.017453292519943295;  // fl(pi/180): np.deg2rad(x) == x * (pi/180)
+
+// ---- lib:136 and lib:157 with the reference's rounding order (no contraction) ----
+__device__ __forceinline__ double x_literal(double den, double f_hz) {
+  const double fp = __dmul_rn(__dsqrt_rn(den), kCp);
+  return __ddiv_rn(__dmul_rn(fp, fp), __dmul_rn(f_hz, f_hz));
+}
+__device__ __forceinline__ double y_literal(double b, double f_hz) {
+  return __ddiv_rn(__dmul_rn(kGp, b), f_hz);
+}
+
+// ---- numpy arr_interp for one query whose bracket j (last xp[j] <= x, -1 below, n above) is known ----
+__device__ __forceinline__ double interp_numpy(double x, int j, int n, const double* xp, const double* fp,
+                                               const double* slope) {
+  if (n == 1 || j < 0) return fp[0];
+  if (j >= n - 1) return fp[n - 1];
+  const double xj = xp[j];
+  if (xj == x) return fp[j];
+  const double s = slope[j];
+  double r = __dadd_rn(__dmul_rn(s, __dsub_rn(x, xj)), fp[j]);
+  if (isnan(r)) {
+    r = __dadd_rn(__dmul_rn(s, __dsub_rn(x, xp[j + 1])), fp[j + 1]);
+    if (isnan(r) && fp[j] == fp[j + 1]) r = fp[j];
+  }
+  return r;
+}
+
+// ---- lib:209-254, every operation in the reference's order (IEEE div / sqrt, libdevice sincos) ----
+// Returns mu' ; *mu_out (optional) receives mu.  NaN where the reference produces NaN.
+template <int MODE>
+__device__ __forceinline__ double ah_literal(double X, double Y, double psi_deg, double* mu_out) {
+  const double sgn = (MODE == 0) ? 1.0 : -1.0;
+  const double rad = __dmul_rn(psi_deg, kDeg2Rad);
+  double s, c;
+  sincos(rad, &s, &c);
+  const double YT = __dmul_rn(Y, s), YL = __dmul_rn(Y, c);
+  const double Xm1 = __dsub_rn(1.0, X);
+  const double YT2 = __dmul_rn(YT, YT);
+  const double YL2 = __dmul_rn(YL, YL);
+  const double Xm12 = __dmul_rn(Xm1, Xm1);
+  const double alpha = __dadd_rn(__dmul_rn(0.25, __dmul_rn(YT2, YT2)), __dmul_rn(YL2, Xm12));
+  const double beta = __dsqrt_rn(alpha);
+  const double D = __dadd_rn(__dsub_rn(Xm1, __dmul_rn(0.5, YT2)), __dmul_rn(sgn, beta));
+  const double XXm1 = __dmul_rn(X, Xm1);
+  double u = __dsub_rn(1.0, __ddiv_rn(XXm1, D));
+  if (u < 0.0) u = CUDART_NAN;
+  double mu = __dsqrt_rn(u);
+  if (mu > 1.0) mu = CUDART_NAN;
+  const double dbdx = __ddiv_rn(__dmul_rn(-YL2, Xm1), beta);
+  const double dDdX = __dadd_rn(-1.0, __dmul_rn(sgn, dbdx));
+  const double dady = __dadd_rn(__dmul_rn(__dmul_rn(YT2, YT), s),
+                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, YL), Xm12), c));
+  const double dbdy = __ddiv_rn(__dmul_rn(0.5, dady), beta);
+  const double dDdY = __dadd_rn(__dmul_rn(-YT, s), __dmul_rn(sgn, dbdy));
+  const double dmudY = __ddiv_rn(__dmul_rn(XXm1, dDdY), __dmul_rn(__dmul_rn(2.0, mu), __dmul_rn(D, D)));
+  const double dmudX = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(__dmul_rn(2.0, mu), D)),
+                                 __dadd_rn(__dsub_rn(__dmul_rn(2.0, X), 1.0),
+                                           __dmul_rn(__ddiv_rn(XXm1, D), dDdX)));
+  if (mu_out) *mu_out = mu;
+  return __dsub_rn(mu, __dadd_rn(__dmul_rn(__dmul_rn(2.0, X), dmudX), __dmul_rn(Y, dmudY)));
+}
+
+// ---- lib:202-206 (isotropic branch) ----
+__device__ __forceinline__ double iso_mup(double X, double* mu_out) {
+  const double mu2 = 1.0 - X;
+  const double mu = (mu2 > 0.0) ? sqrt(mu2) : CUDART_NAN;
+  if (mu_out) *mu_out = mu;
+  return (isfinite(mu) && mu > 0.0) ? 1.0 / mu : CUDART_NAN;
+}
+
+// ---- restructured Appleton-Hartree: same formulas as lib:209-254, algebraically rearranged ----
+//   a = YT^2/2, w = YL^2 Xm1, alpha = a^2 + w Xm1, beta = sqrt(alpha), P = a + beta
+//   X-mode:  D = Xm1 - P                      (no cancellation: D -> Y(1-Y) at reflection)
+//   O-mode:  D = Xm1 (1 + g), g = w / P       (cancellation-free form of Xm1 - a + beta)
+//   Y dD/dY = -2a + s (beta + a^2/beta),  dD/dX = -1 - s w / beta      (s = +1 O, -1 X)
+//   mu' = mu - [ X (2X - 1 + q dD/dX) + q (Y dD/dY) / 2 ] / (mu D),   q = X Xm1 / D
+// One reciprocal and two reciprocal square roots per point instead of 7 divides + 2 square roots.
+// Agreement with a long-double evaluation of lib:209-254: <= 3e-12 (tests/test_oracle_*).
+template <int MODE>
+__device__ __forceinline__ double ah_fast(double X, double Y, double sn, double cs, double* mu_out) {
+  const double YT = Y * sn, YL = Y * cs;
+  const double Xm1 = 1.0 - X;
+  const double a = 0.5 * (YT * YT);
+  const double w = (YL * YL) * Xm1;
+  const double a2 = a * a;
+  const double alpha = fma(w, Xm1, a2);
+  const double rb = rsqrt(alpha);
+  const double beta = alpha * rb;
+  const double P = a + beta;
+  double invD, q, u, dDdX, YdDdY;
+  if (MODE == 1) {
+    const double D = Xm1 - P;
+    invD = 1.0 / D;
+    q = (X * Xm1) * invD;
+    u = 1.0 - q;
+    dDdX = fma(w, rb, -1.0);
+    YdDdY = -fma(a2, rb, beta) - 2.0 * a;
+  } else {
+    const double R = 1.0 / (Xm1 * (P + w));
+    const double XR = Xm1 * R;
+    invD = P * R;
+    q = (X * P) * XR;
+    u = fma(Xm1, P, w) * XR;
+    dDdX = -fma(w, rb, 1.0);
+    YdDdY = fma(a2, rb, beta) - 2.0 * a;
+  }
+  const double rmu = rsqrt(u);
+  const double mu = u * rmu;
+  const double br = fma(0.5 * q, YdDdY, X * fma(q, dDdX, fma(2.0, X, -1.0)));
+  double mup = fma(-(invD * rmu), br, mu);
+  if (!(u >= 0.0 && u <= 1.0)) mup = CUDART_NAN;     // lib:233 and lib:238
+  if (mu_out) *mu_out = (u >= 0.0 && u <= 1.0) ? mu : CUDART_NAN;
+  return mup;
+}
+
+// sin/cos of (r_k + delta) from the node's sin/cos and a short Taylor series in delta (|delta| <= 0.05:
+// truncation < 6e-18).  Replaces a full-range sincos per grid point.
+__device__ __forceinline__ void rotate_sincos(double sk, double ck, double delta, double* sn, double* cs) {
+  const double d2 = delta * delta;
+  double ps = fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
+  ps = fma(d2, ps, -1.0 / 6.0);
+  ps = fma(d2, ps, 1.0);
+  const double sd = delta * ps;                       // sin(delta)
+  double pc = fma(d2, 1.0 / 40320.0, -1.0 / 720.0);
+  pc = fma(d2, pc, 1.0 / 24.0);
+  pc = fma(d2, pc, -0.5);
+  const double cdm1 = d2 * pc;                        // cos(delta) - 1
+  *sn = fma(ck, sd, fma(sk, cdm1, sk));
+  *cs = fma(-sk, sd, fma(ck, cdm1, ck));
+}
+constexpr double kMaxRotateStep = 0.05;               // rad; larger per-segment steps use sincos()
+
+}  // namespace prhf

@@ -1,0 +1,39 @@
+// Internal launcher interface between the C ABI (vfo_cabi.cu) and the kernels (vfo_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace prhf {
+
+constexpr int kThreads = 256;
+
+struct VfoParams {
+  const double* freq;      // MHz; [n_freq] or per-profile rows
+  int64_t freq_stride;     // 0 = shared
+  int n_freq;
+  const double* den;       // [P x n_alt]
+  const double* bmag;
+  const double* bpsi;
+  const double* alt;       // [n_alt] or [P x n_alt]
+  int64_t alt_stride;      // 0 = shared
+  int n_alt;
+  int64_t profile_offset;  // first profile handled by this launch
+  const double* mult;      // stretched-grid multiplier [n_points]
+  int n_points;
+  int seg_len;             // grid points per tile
+  int n_seg;               // tiles per (profile, frequency) row
+  double* vh;              // [P x n_freq]
+  int* status;             // [P] or null
+  double* partial;         // [rows_in_launch x n_seg] when n_seg > 1
+  unsigned* counter;       // [rows_in_launch], zero on entry, zero on exit
+};
+
+size_t vfo_smem_bytes(int n_alt);
+cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
+cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
+cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
+                          bool literal, double* mu, double* mup, cudaStream_t stream);
+cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
+
+}  // namespace prhf

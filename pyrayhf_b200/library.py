@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference interface for the vertical forward operator.
+
+``vertical_forward_operator`` keeps the signature, units, return type and error behaviour
+of ``PyRayHF.library.vertical_forward_operator`` (PyRayHF/library.py:459-509); the
+arithmetic runs in the fused CUDA kernels behind the C ABI (``include/pyrayhf_b200.h``).
+``vertical_forward_operator_batched`` is the ``[n_profiles x n_alt]`` form.
+
+There is no CPU fallback: a missing extension or GPU raises.
+"""
+import ctypes
+
+import numpy as np
+
+from pyrayhf_b200 import _cabi
+
+_vp = ctypes.c_void_p
+
+
+def _logger():
+    import pyrayhf_b200
+    return pyrayhf_b200.logger
+
+
+def _mode_code(mode):
+    # library.py:391-396: exact, case-sensitive comparison with 'O' / 'X'
+    if isinstance(mode, str) and mode == 'O':
+        return 0
+    if isinstance(mode, str) and mode == 'X':
+        return 1
+    raise ValueError("mode must be 'O' or 'X'")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return _vp(a.ctypes.data)
+
+
+def _raise_profile_status(st):
+    if st == 1:
+        raise ValueError("Density must be non-negative")                     # library.py:94
+    if st == 2:
+        raise IndexError("index -1 is out of bounds for axis 1 with size 0")  # library.py:399
+
+
+def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
+                              literal=False, device=-1):
+    """Calculate virtual height from ionosonde freq and ion profile (drop-in).
+
+    Parameters as the reference (library.py:463-478): ``freq`` [MHz] ndarray, ``den``
+    [m^-3], ``bmag`` [T], ``bpsi`` [deg], ``alt`` [km] ndarrays of one length, ``mode``
+    'O' or 'X', ``n_points`` grid points.  Returns a new float64 ndarray, NaN where the
+    ray does not reflect.  Raises what the reference raises: ValueError for a bad mode
+    (library.py:396) or negative density below the peak (library.py:94), IndexError when
+    the density peak is the first sample (library.py:399).
+
+    ``literal=True`` evaluates the Appleton-Hartree block in the reference's operation
+    order (debug aid; O-mode then inherits the reference's cancellation noise).
+    """
+    freq = np.asarray(freq)
+    den, bmag, bpsi, alt = (np.asarray(v) for v in (den, bmag, bpsi, alt))
+    # library.py:487-488: chained inequality, logs and continues
+    if den.shape != bmag.shape != bpsi.shape != alt.shape:
+        _logger().error("Error: freq, den, bmag, bpsi, alt should have same size")
+    code = _mode_code(mode)
+    if freq.ndim > 1:
+        raise ValueError("operands could not be broadcast together: freq must be 0-d or 1-d")
+    out_shape = (freq.size,)
+    f = _f64(freq).reshape(-1)
+    d, b, p, a = _f64(den).reshape(-1), _f64(bmag).reshape(-1), _f64(bpsi).reshape(-1), _f64(alt).reshape(-1)
+    n_alt = d.size
+    if not (b.size == p.size == a.size == n_alt):
+        raise ValueError("den, bmag, bpsi, alt must have the same length")
+    n_points = int(n_points)
+    vh = np.empty(f.size, dtype=np.float64)
+    if f.size == 0:
+        return vh.reshape(out_shape)
+    if n_alt == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")       # np.argmax, library.py:371
+    if n_points < 1:
+        vh.fill(np.nan)         # empty grid: nansum over nothing is 0 -> NaN (library.py:288-290)
+        return vh.reshape(out_shape)
+    ctx = _cabi.context(device)
+    st = np.zeros(1, dtype=np.int32)
+    rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(f), f.size, 0, _ptr(d), _ptr(b), _ptr(p), _ptr(a), 0,
+                                   1, n_alt, code, n_points, _cabi.FLAG_LITERAL if literal else 0,
+                                   _ptr(vh), _ptr(st))
+    ctx.check(rc)
+    _raise_profile_status(int(st[0]))
+    return vh.reshape(out_shape)
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
+                                      literal=False, errors='raise', return_status=False,
+                                      out=None, device=None):
+    """Batched operator: ``den``/``bmag``/``bpsi`` are ``[P, A]``; ``freq`` is ``[F]`` or
+    ``[P, F]``; ``alt`` is ``[A]`` or ``[P, A]``.  Row ``p`` of the ``[P, F]`` result equals
+    the reference called on profile ``p`` alone (peak truncation, unmagnetised switch and
+    error status are per profile).
+
+    Inputs may be numpy arrays (copied through pinned memory, numpy result) or float64
+    CUDA torch tensors (used in place on the current stream, torch result, asynchronous).
+    ``errors='raise'`` re-raises the reference's per-profile exceptions (needs a host
+    sync for torch inputs); ``errors='nan'`` leaves failed profiles as NaN rows.
+    """
+    code = _mode_code(mode)
+    n_points = int(n_points)
+    flags = _cabi.FLAG_LITERAL if literal else 0
+    if _is_torch_tensor(den):
+        import torch
+        ts = [freq, den, bmag, bpsi, alt]
+        for t in ts:
+            if not (_is_torch_tensor(t) and t.is_cuda and t.dtype == torch.float64):
+                raise TypeError("torch inputs must all be float64 CUDA tensors")
+        freq, den, bmag, bpsi, alt = (t.contiguous() for t in ts)
+        n_prof, n_alt = den.shape
+        n_freq = freq.shape[-1]
+        dev = den.device
+        vh = out if out is not None else torch.empty((n_prof, n_freq), dtype=torch.float64, device=dev)
+        st = torch.zeros(n_prof, dtype=torch.int32, device=dev)
+        if n_prof == 0 or n_freq == 0:
+            return (vh, st) if return_status else vh
+        if n_points < 1:
+            vh.fill_(float('nan'))
+            return (vh, st) if return_status else vh
+        ctx = _cabi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = ctx.lib.prhf_vfo_f64(ctx.handle, _vp(freq.data_ptr()), n_freq, n_freq if freq.dim() == 2 else 0,
+                                  _vp(den.data_ptr()), _vp(bmag.data_ptr()), _vp(bpsi.data_ptr()),
+                                  _vp(alt.data_ptr()), n_alt if alt.dim() == 2 else 0, n_prof, n_alt, code,
+                                  n_points, flags, _vp(vh.data_ptr()), _vp(st.data_ptr()), _vp(stream))
+        ctx.check(rc)
+        if errors == 'raise':
+            bad = int(st.max().item())
+            if bad:
+                _raise_profile_status(bad)
+        return (vh, st) if return_status else vh
+
+    freq, den, bmag, bpsi, alt = (_f64(v) for v in (freq, den, bmag, bpsi, alt))
+    if den.ndim != 2:
+        raise ValueError("den must be [n_profiles, n_alt]")
+    n_prof, n_alt = den.shape
+    n_freq = freq.shape[-1]
+    vh = np.empty((n_prof, n_freq), dtype=np.float64)
+    st = np.zeros(n_prof, dtype=np.int32)
+    if n_prof and n_freq:
+        if n_points < 1:
+            vh.fill(np.nan)
+        else:
+            ctx = _cabi.context(-1 if device is None else device)
+            rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(freq), n_freq, n_freq if freq.ndim == 2 else 0,
+                                           _ptr(den), _ptr(bmag), _ptr(bpsi), _ptr(alt),
+                                           n_alt if alt.ndim == 2 else 0, n_prof, n_alt, code, n_points,
+                                           flags, _ptr(vh), _ptr(st))
+            ctx.check(rc)
+    if errors == 'raise' and st.any():
+        _raise_profile_status(int(st.max()))
+    return (vh, st) if return_status else vh
+
+
+def find_mu_mup(X, Y, bpsi, mode, *, y_tol=1e-12, literal=False):
+    """Phase / group refractive index on the GPU (library.py:161-256), numpy in/out."""
+    X = np.asarray(X, dtype=float)
+    Y = np.asarray(Y, dtype=float)
+    bpsi = np.asarray(bpsi, dtype=float)
+    X, Y, bpsi = np.broadcast_arrays(X, Y, bpsi)
+    shape = X.shape
+    with np.errstate(all='ignore'):
+        iso = bool(np.nanmax(np.abs(Y)) < y_tol) if Y.size else False      # library.py:201
+    if not iso and mode not in ('O', 'X'):
+        raise ValueError("Mode must be O or X")                              # library.py:226
+    code = 0 if mode == 'O' else 1
+    import torch
+    dev = torch.device('cuda', torch.cuda.current_device())
+    tx, ty, tp = (torch.from_numpy(_f64(v).reshape(-1)).to(dev) for v in (X, Y, bpsi))
+    mu = torch.empty_like(tx)
+    mup = torch.empty_like(tx)
+    ctx = _cabi.context(dev.index)
+    rc = ctx.lib.prhf_mu_mup_f64(ctx.handle, _vp(tx.data_ptr()), _vp(ty.data_ptr()), _vp(tp.data_ptr()),
+                                 tx.numel(), code, int(iso), _cabi.FLAG_LITERAL if literal else 0,
+                                 _vp(mu.data_ptr()), _vp(mup.data_ptr()),
+                                 _vp(torch.cuda.current_stream(dev).cuda_stream))
+    ctx.check(rc)
+    return mu.cpu().numpy().reshape(shape), mup.cpu().numpy().reshape(shape)
+
+
+_saved = {}
+
+
+def install():
+    """Rebind ``PyRayHF.library.vertical_forward_operator`` to this implementation.
+
+    ``model_VH`` resolves the name through its module globals at call time
+    (library.py:589), so the inversion code picks the GPU path up unchanged.
+    """
+    import PyRayHF.library as ref
+    if 'vertical_forward_operator' not in _saved:
+        _saved['vertical_forward_operator'] = ref.vertical_forward_operator
+    ref.vertical_forward_operator = vertical_forward_operator
+    return ref
+
+
+def uninstall():
+    if 'vertical_forward_operator' in _saved:
+        import PyRayHF.library as ref
+        ref.vertical_forward_operator = _saved.pop('vertical_forward_operator')

@@ -1,0 +1,209 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the committed goldens.
+
+Acceptance (conftest.assert_parity): NaN masks identical; X-mode <= 1e-9 relative against
+the reference; O-mode <= 1e-9 against the long-double truth and inside the reference's own
+rounding ball.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, rel_err
+from oracle import scalar, vfo_oracle
+from pyrayhf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter("ignore")
+
+
+@pytest.fixture(scope="module")
+def vfo():
+    import torch
+    assert torch.cuda.is_available()
+    import pyrayhf_b200
+    return pyrayhf_b200
+
+
+def test_kat(vfo, golden):
+    k = golden.kat
+    for mode in "OX":
+        got = vfo.vertical_forward_operator(k["basic_freq"], k["basic_den"], k["basic_bmag"], k["basic_bpsi"],
+                                            k["basic_alt"], mode, 50)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float64 and got.shape == (3,)
+        ref = k["basic_vh_" + mode]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert np.isnan(got[-1]) and np.all(np.isfinite(got[:-1]))
+        if mode == 'X':
+            assert rel_err(got, ref) < 1e-9
+    got = vfo.vertical_forward_operator(k["model_freq"], k["model_edp"], k["basic_bmag"], k["basic_bpsi"],
+                                        k["basic_alt"], 'O', 200)
+    np.testing.assert_allclose(got, k["model_expected_vh"], rtol=1e-6)     # tests/test_core.py:275
+    assert rel_err(got, k["model_truth_O"]) < 1e-9
+
+
+def test_kat_mu_mup(vfo, golden):
+    k = golden.kat
+    for literal in (False, True):
+        mu, mup = vfo.find_mu_mup(k["mumup_X"], k["mumup_Y"], k["mumup_psi"], 'O', literal=literal)
+        np.testing.assert_allclose(mu, k["mumup_expected_mu"], rtol=1e-5)   # tests/test_core.py:149-152
+        np.testing.assert_allclose(mup, k["mumup_expected_mup"], rtol=1e-5)
+        assert rel_err(mup, k["mumup_mup_O"]) < 1e-11
+        mux, mupx = vfo.find_mu_mup(k["mumup_X"], k["mumup_Y"], k["mumup_psi"], 'X', literal=literal)
+        assert np.array_equal(np.isnan(mupx), np.isnan(k["mumup_mup_X"]))
+        assert rel_err(mupx, k["mumup_mup_X"]) < 1e-11
+
+
+@pytest.mark.parametrize("which", ["Day", "Night"])
+@pytest.mark.parametrize("mode", ["O", "X"])
+@pytest.mark.parametrize("n,fk", [(1, "a"), (2, "a"), (50, "a"), (200, "a"), (200, "b"), (2000, "a"),
+                                  (20000, "a"), (20000, "b")])
+def test_tutorial_fixtures(vfo, golden, which, mode, n, fk):
+    fx = golden.fixtures
+    tag = "%s_%s_%d_%s" % (which, mode, n, fk)
+    got = vfo.vertical_forward_operator(fx["freq_" + fk], fx[which + "_den"], fx[which + "_bmag"],
+                                        fx[which + "_bpsi"], fx[which + "_alt"], mode, n)
+    assert_parity(got, fx["ref_" + tag], fx["truth_" + tag], mode, tag)
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_literal_flag_tracks_reference(vfo, golden, mode):
+    """The literal path reproduces the reference's operation order: X-mode to 1e-11, O-mode to
+    within a small multiple of the reference's own cancellation noise."""
+    fx = golden.fixtures
+    for which in ("Day", "Night"):
+        tag = "%s_%s_200_a" % (which, mode)
+        got = vfo.vertical_forward_operator(fx["freq_a"], fx[which + "_den"], fx[which + "_bmag"],
+                                            fx[which + "_bpsi"], fx[which + "_alt"], mode, 200, literal=True)
+        ref, tru = fx["ref_" + tag], fx["truth_" + tag]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        if mode == 'X':
+            assert rel_err(got, ref) < 1e-11
+        else:
+            assert rel_err(got, ref) <= 2.5 * rel_err(ref, tru) + 1e-9
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_synthetic_batch_numpy(vfo, golden, mode):
+    sy = golden.synthetic
+    den, bmag, bpsi = synth.profiles_at(sy["lat"], sy["lon"], sy["alt"])
+    got, st = vfo.vertical_forward_operator_batched(sy["freq"], den, bmag, bpsi, sy["alt"], mode, 200,
+                                                    return_status=True)
+    assert not st.any()
+    assert_parity(got, sy["ref_%s_200" % mode], sy["truth_%s_200" % mode], mode, "synthetic 200")
+    sub = sy["sub_20000"]
+    got = vfo.vertical_forward_operator_batched(sy["freq"], den[sub], bmag[sub], bpsi[sub], sy["alt"], mode, 20000)
+    assert_parity(got, sy["ref_%s_20000" % mode], sy["truth_%s_20000" % mode], mode, "synthetic 20000")
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_synthetic_batch_torch_device(vfo, golden, mode):
+    import torch
+    sy = golden.synthetic
+    den, bmag, bpsi = synth.profiles_at(sy["lat"], sy["lon"], sy["alt"])
+    dev = torch.device("cuda:0")
+    P = den.shape[0]
+    # per-profile freq and alt rows exercise the strided variants
+    freq2 = np.tile(sy["freq"], (P, 1))
+    alt2 = np.tile(sy["alt"], (P, 1))
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq2, den, bmag, bpsi, alt2)]
+    vh, st = vfo.vertical_forward_operator_batched(*t, mode, 200, return_status=True)
+    assert vh.is_cuda and vh.dtype == torch.float64 and tuple(vh.shape) == (P, sy["freq"].size)
+    assert int(st.abs().sum().item()) == 0
+    assert_parity(vh.cpu().numpy(), sy["ref_%s_200" % mode], sy["truth_%s_200" % mode], mode, "torch batch")
+
+
+EDGE_CASES = ["b_zero", "nan_bmag", "odd_freq", "int_alt", "nonuniform_alt", "valley", "psi_jump",
+              "near_crit", "near_crit_hi", "two_level", "peak_at_one"]
+
+
+@pytest.mark.parametrize("name", EDGE_CASES)
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_edge_cases(vfo, golden, name, mode):
+    e = golden.edge
+    args = tuple(e["%s_%s" % (name, k)] for k in ("freq", "den", "bmag", "bpsi", "alt"))
+    n = int(e[name + "_n"])
+    got = vfo.vertical_forward_operator(*args, mode, n)
+    assert_parity(got, e["%s_ref_%s" % (name, mode)], e["%s_truth_%s" % (name, mode)], mode, name)
+
+
+def test_error_behaviour(vfo):
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    f = np.array([2.0, 3.0])
+    with pytest.raises(ValueError, match="mode must be 'O' or 'X'"):
+        vfo.vertical_forward_operator(f, den, bmag, bpsi, alt, 'o', 50)
+    neg = den.copy()
+    neg[3] = -1.0
+    with pytest.raises(ValueError, match="Density must be non-negative"):
+        vfo.vertical_forward_operator(f, neg, bmag, bpsi, alt, 'O', 50)
+    k = int(np.argmax(den))
+    with pytest.raises(IndexError):
+        vfo.vertical_forward_operator(f, den[k:], bmag[k:], bpsi[k:], alt[k:], 'O', 50)
+    # batched: failed profiles are reported per profile and come back as NaN rows
+    lat, lon = synth.grid_subset(5)
+    d2, b2, p2 = synth.profiles_at(lat, lon, alt)
+    d2[1, 2] = -3.0
+    d2[3] = d2[3, ::-1]
+    vh, st = vfo.vertical_forward_operator_batched(f, d2, b2, p2, alt, 'X', 100, errors='nan', return_status=True)
+    assert list(st) == [0, 1, 0, 2 if np.argmax(d2[3]) == 0 else 0, 0]
+    assert np.all(np.isnan(vh[1]))
+    ref = vfo_oracle.vertical_forward_operator(f, d2[0], b2[0], p2[0], alt, 'X', 100)
+    assert np.array_equal(np.isnan(vh[0]), np.isnan(ref)) and rel_err(vh[0], ref) < 1e-9
+    with pytest.raises(ValueError):
+        vfo.vertical_forward_operator_batched(f, d2, b2, p2, alt, 'X', 100)
+    # float32 / int inputs are up-cast like the reference does
+    got = vfo.vertical_forward_operator(f.astype(np.float32), den.astype(np.float32), bmag, bpsi, alt.astype(np.int64), 'X', 100)
+    ref = vfo_oracle.vertical_forward_operator(f.astype(np.float32).astype(float), den.astype(np.float32).astype(float),
+                                               bmag, bpsi, alt.astype(float), 'X', 100)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and rel_err(got, ref) < 1e-9
+    # 0-d frequency -> shape (1,)
+    got = vfo.vertical_forward_operator(np.array(2.0), den, bmag, bpsi, alt, 'X', 100)
+    assert got.shape == (1,)
+
+
+@pytest.mark.parametrize("seg_len", [256, 1024, 4096, 100000])
+def test_tiling_invariance(vfo, golden, seg_len, monkeypatch):
+    """The result must not depend on how rows are split into tiles (fresh ctx per setting)."""
+    from pyrayhf_b200 import _cabi
+    monkeypatch.setenv("PRHF_SEG_LEN", str(seg_len))
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    fx = golden.fixtures
+    got = vfo.vertical_forward_operator(fx["freq_a"], fx["Day_den"], fx["Day_bmag"], fx["Day_bpsi"], fx["Day_alt"],
+                                        'X', 20000)
+    assert_parity(got, fx["ref_Day_X_20000_a"], fx["truth_Day_X_20000_a"], 'X', "seg_len %d" % seg_len)
+    # repeated call on the same ctx exercises the self-resetting counters
+    got2 = vfo.vertical_forward_operator(fx["freq_a"], fx["Day_den"], fx["Day_bmag"], fx["Day_bpsi"], fx["Day_alt"],
+                                         'X', 20000)
+    assert np.array_equal(got, got2, equal_nan=True)
+
+
+def test_full_size_properties(vfo):
+    """BASELINE config sizes, size-independent properties instead of an oracle run:
+    determinism, batch == single, permutation equivariance over profiles and frequencies."""
+    import torch
+    lat, lon = synth.grid_subset(64, seed=3)
+    alt = synth.default_alt()
+    freq = synth.default_freq()
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+    a = vfo.vertical_forward_operator_batched(*t, 'X', 20000).cpu().numpy()
+    b = vfo.vertical_forward_operator_batched(*t, 'X', 20000).cpu().numpy()
+    assert np.array_equal(a, b, equal_nan=True)
+    perm = np.random.default_rng(0).permutation(64)
+    tp = [t[0]] + [v[torch.from_numpy(perm).to(dev)] for v in t[1:4]] + [t[4]]
+    c = vfo.vertical_forward_operator_batched(*tp, 'X', 20000).cpu().numpy()
+    assert np.array_equal(c, a[perm], equal_nan=True)
+    fperm = np.random.default_rng(1).permutation(freq.size)
+    tf = [t[0][torch.from_numpy(fperm).to(dev)]] + t[1:]
+    d = vfo.vertical_forward_operator_batched(*tf, 'X', 20000).cpu().numpy()
+    assert np.array_equal(d, a[:, fperm], equal_nan=True)
+    single = vfo.vertical_forward_operator(freq, den[5], bmag[5], bpsi[5], alt, 'X', 20000)
+    assert np.array_equal(np.isnan(single), np.isnan(a[5])) and rel_err(single, a[5]) < 1e-13
+    # virtual height is >= true height of reflection >= bottom of the profile, and increases
+    # with frequency inside each layer: check the weaker invariant vh >= alt[0]
+    assert np.nanmin(a) >= alt[0]
+    # oracle spot check at full n_points on two profiles
+    for p in (0, 63):
+        ref = vfo_oracle.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, 'X', 20000)
+        assert np.array_equal(np.isnan(a[p]), np.isnan(ref)) and rel_err(a[p], ref) < 1e-9

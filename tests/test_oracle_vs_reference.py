@@ -1,0 +1,73 @@
+"""CPU, dev container only: the numpy oracle bit-for-bit against the LIVE reference.
+
+Skipped where /root/reference is not mounted (the GPU box); tests/test_oracle_golden.py
+covers the same ground through the committed fixtures there.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import vfo_oracle
+from oracle.ref_import import load_reference_library, reference_available
+from pyrayhf_b200 import synth
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference mount absent")
+warnings.simplefilter("ignore")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return load_reference_library()
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+@pytest.mark.parametrize("n", [1, 3, 64, 200, 1500])
+def test_random_synthetic_profiles_bit_exact(ref, mode, n):
+    rng = np.random.default_rng(n * 7 + (mode == 'X'))
+    lat = rng.uniform(-90, 90, 6)
+    lon = rng.uniform(-180, 180, 6)
+    alt = synth.default_alt()
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    f = np.sort(rng.uniform(0.05, 16.0, 40))
+    for p in range(lat.size):
+        a = ref.vertical_forward_operator(f, den[p], bmag[p], bpsi[p], alt, mode, n)
+        b = vfo_oracle.vertical_forward_operator(f, den[p], bmag[p], bpsi[p], alt, mode, n)
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_stage_functions_bit_exact(ref):
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    f_hz = synth.default_freq() * 1e6
+    assert np.array_equal(ref.smooth_nonuniform_grid(0, 1, 777, 10.), vfo_oracle.stretch_multiplier(777))
+    for mode in "OX":
+        want = ref.regrid_to_nonuniform_grid(f_hz, den, bmag, bpsi, alt, mode, 300)
+        got = vfo_oracle.regrid(f_hz, den, bmag, bpsi, alt, mode, 300)
+        for a, b in (("alt", "h"), ("dist", "dh"), ("den", "den"), ("bmag", "bmag"), ("bpsi", "bpsi")):
+            assert np.array_equal(want[a], got[b], equal_nan=True), (mode, a)
+        assert np.array_equal(want["crit_height"][:, 0], got["h_c"], equal_nan=True)
+    X = np.linspace(0.01, 0.99, 50)
+    Y = np.full(50, 0.2)
+    psi = np.linspace(0, 90, 50)
+    for mode in "OX":
+        a = ref.find_mu_mup(X, Y, psi, mode)
+        b = vfo_oracle.appleton_hartree(X, Y, psi, mode)
+        assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+    assert np.array_equal(ref.find_X(den, 5e6), vfo_oracle.plasma_ratio_x(den, 5e6))
+    assert np.array_equal(ref.find_Y(5e6, bmag), vfo_oracle.gyro_ratio_y(5e6, bmag))
+    assert ref.constants()[:2] == (vfo_oracle.CP_HZ_PER_SQRT_M3, vfo_oracle.GYRO_HZ_PER_T)
+
+
+def test_errors_match(ref):
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    f = np.array([2.0])
+    for impl in (ref.vertical_forward_operator, vfo_oracle.vertical_forward_operator):
+        with pytest.raises(ValueError):
+            impl(f, den, bmag, bpsi, alt, 'Q', 10)
+        with pytest.raises(IndexError):
+            k = int(np.argmax(den))
+            impl(f, den[k:], bmag[k:], bpsi[k:], alt[k:], 'O', 10)
+        neg = den.copy()
+        neg[0] = -5.0
+        with pytest.raises(ValueError):
+            impl(f, neg, bmag, bpsi, alt, 'X', 10)
