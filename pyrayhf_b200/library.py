@@ -75,13 +75,14 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
         raise ValueError("den, bmag, bpsi, alt must have the same length")
     n_points = int(n_points)
     vh = np.empty(f.size, dtype=np.float64)
-    if f.size == 0:
-        return vh.reshape(out_shape)
     if n_alt == 0:
         raise ValueError("attempt to get argmax of an empty sequence")       # np.argmax, library.py:371
+    if f.size == 0:
+        # np.apply_along_axis at library.py:403 refuses a zero-length frequency axis
+        raise ValueError("Cannot apply_along_axis when any iteration dimensions are 0")
     if n_points < 1:
-        vh.fill(np.nan)         # empty grid: nansum over nothing is 0 -> NaN (library.py:288-290)
-        return vh.reshape(out_shape)
+        # np.nanmax of an empty [F x 0] array at library.py:201
+        raise ValueError("zero-size array to reduction operation fmax which has no identity")
     ctx = _cabi.context(device)
     st = np.zeros(1, dtype=np.int32)
     rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(f), f.size, 0, _ptr(d), _ptr(b), _ptr(p), _ptr(a), 0,
