@@ -95,3 +95,17 @@ def ensemble_member(lat_deg, lon_deg, member, alt=None):
     # NmF2 * exp(0.10 xi1)  <=>  foF2 * exp(0.05 xi1)
     return profiles_from_parameters(fof2 * np.exp(0.05 * xi[0]), hmf2 + 10.0 * xi[1],
                                     scale_h * np.exp(0.05 * xi[2]), foe, lat_deg, alt)
+
+
+def bench_day_profile(alt=None, rank=0):
+    """Benchmark profile for BASELINE configs[1]: day side of the parameter map (lat 4.5, lon 0).
+
+    foF2 = 12.9 MHz, so 129 of the 174 sounding frequencies reflect (the real tutorial Day profile:
+    133 of 174).  SURVEY.md 8d's (4.5, -150) point sits on the night side of its own map
+    (foF2 = 4.6 MHz, 41 of 174 rows reflect) and would flatter a virtual-heights/s figure, because
+    rows that never reflect cost the GPU almost nothing.  ``rank`` shifts the longitude by one degree
+    per rank so that every GPU of a multi-GPU run owns a different profile.
+    """
+    alt = default_alt() if alt is None else alt
+    den, bmag, bpsi = profiles_at([4.5], [0.0 + float(rank)], alt)
+    return den[0], bmag[0], bpsi[0], alt

@@ -51,6 +51,11 @@ def time_device(P, mode, n, reps=10, literal=False):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--case":
+        P, mode, n = int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
+        reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+        print(json.dumps(time_device(P, mode, n, reps=reps)))
+        return
     ctx = _cabi.context(0)
     print(json.dumps({"fp64_peak_tflops": ctx.measure_fp64_peak()}))
     for args in [(1, 'X', 20000), (1, 'O', 20000), (1, 'X', 200), (64, 'X', 20000), (512, 'X', 20000),
