@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "prhf_version", "prhf_error_string", "prhf_last_cuda_error", "prhf_ctx_create",
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
     "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
+    "prhf_selftest_math",
 )
 
 _vp = ctypes.c_void_p
@@ -78,6 +79,8 @@ def load():
         L.prhf_mu_mup_f64.restype = _i
         L.prhf_measure_fp64_peak.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
         L.prhf_measure_fp64_peak.restype = _i
+        L.prhf_selftest_math.argtypes = [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.prhf_selftest_math.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L
@@ -133,6 +136,11 @@ class Context:
 
     def launch_count(self):
         return self._L.prhf_launch_count(self._h)
+
+    def selftest_math(self):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self.check(self._L.prhf_selftest_math(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def measure_fp64_peak(self):
         out = ctypes.c_double()

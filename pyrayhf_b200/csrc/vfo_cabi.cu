@@ -28,6 +28,10 @@ struct prhf_ctx {
   double* partial = nullptr;
   unsigned* counter = nullptr;
   size_t partial_cap = 0, counter_cap = 0;
+  // K1 -> K2 hand-off: one ProfileRecord per profile, one double per (profile, frequency) row
+  prhf::ProfileRecord* prof_rec = nullptr;
+  double* row_span = nullptr;
+  size_t prof_cap = 0, row_cap = 0;
   // host entry: device arena + pinned mirror + private stream
   cudaStream_t stream = nullptr;
   char* d_arena = nullptr;
@@ -72,7 +76,7 @@ int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const doubl
     return PRHF_OK;
   }
   double* m = nullptr;
-  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * (size_t)n_points));
+  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * ((size_t)n_points + prhf::kMultPad)));
   cudaError_t e = prhf::launch_grid_multiplier(n_points, m, stream);
   ctx->launches++;
   if (e != cudaSuccess) {
@@ -83,6 +87,24 @@ int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const doubl
   PRHF_CUDA(ctx, cudaStreamSynchronize(stream));
   ctx->mult[n_points] = m;
   *out = m;
+  return PRHF_OK;
+}
+
+int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
+  if (n_prof > ctx->prof_cap) {
+    if (ctx->prof_rec) cudaFree(ctx->prof_rec);
+    ctx->prof_rec = nullptr;
+    ctx->prof_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->prof_rec, sizeof(prhf::ProfileRecord) * n_prof));
+    ctx->prof_cap = n_prof;
+  }
+  if (n_rows > ctx->row_cap) {
+    if (ctx->row_span) cudaFree(ctx->row_span);
+    ctx->row_span = nullptr;
+    ctx->row_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->row_span, sizeof(double) * n_rows));
+    ctx->row_cap = n_rows;
+  }
   return PRHF_OK;
 }
 
@@ -113,6 +135,7 @@ int ensure_workspace(prhf_ctx* ctx, size_t n_partial, size_t n_counter) {
 void choose_tiling(const prhf_ctx* ctx, int64_t rows, int n_points, int* seg_len, int* n_seg) {
   if (ctx->seg_len_override > 0) {
     int sl = std::min(ctx->seg_len_override, std::max(n_points, 1));
+    sl += (sl & 1);          // tiles start on even grid indices (two points per thread per iteration)
     *seg_len = sl;
     *n_seg = (n_points + sl - 1) / sl;
     return;
@@ -199,6 +222,8 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   for (auto& kv : ctx->mult) cudaFree(kv.second);
   if (ctx->partial) cudaFree(ctx->partial);
   if (ctx->counter) cudaFree(ctx->counter);
+  if (ctx->prof_rec) cudaFree(ctx->prof_rec);
+  if (ctx->row_span) cudaFree(ctx->row_span);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -237,13 +262,18 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
   int seg_len = 0, n_seg = 0;
   choose_tiling(ctx, rows_total, n_points, &seg_len, &n_seg);
 
-  // A launch covers at most max_tiles tiles (grid.x limit); profiles are chunked accordingly.
+  // A launch covers at most max_tiles tiles (grid.x limit) and max_rows rows (hand-off workspace);
+  // profiles are chunked accordingly.
   const int64_t max_tiles = (int64_t)1 << 30;
+  const int64_t max_rows = (int64_t)1 << 24;
   const int64_t tiles_per_profile = (int64_t)n_freq * n_seg;
   if (tiles_per_profile > max_tiles) return PRHF_ERR_INVALID_ARG;
-  const int64_t prof_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_profile);
+  int64_t prof_per_launch = std::max<int64_t>(1, std::min(max_tiles / tiles_per_profile, max_rows / n_freq));
+  prof_per_launch = std::min(prof_per_launch, n_profiles);
+  const int64_t rows_launch = prof_per_launch * n_freq;
+  rc = ensure_records(ctx, (size_t)prof_per_launch, (size_t)rows_launch);
+  if (rc != PRHF_OK) return rc;
   if (n_seg > 1) {
-    const int64_t rows_launch = std::min(prof_per_launch, n_profiles) * n_freq;
     rc = ensure_workspace(ctx, (size_t)rows_launch * n_seg, (size_t)rows_launch);
     if (rc != PRHF_OK) return rc;
   }
@@ -266,10 +296,13 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_seg = n_seg;
     P.vh = vh_out;
     P.status = status;
+    P.prof_rec = ctx->prof_rec;
+    P.row_span = ctx->row_span;
     P.partial = ctx->partial;
     P.counter = ctx->counter;
+    PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
     PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, (flags & PRHF_FLAG_LITERAL) != 0, np * tiles_per_profile, stream));
-    ctx->launches++;
+    ctx->launches += 2;
   }
   return PRHF_OK;
 }
@@ -357,6 +390,24 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
   PRHF_CUDA(ctx, prhf::launch_mu_mup(X, Y, bpsi_deg, n, mode, isotropic != 0, (flags & PRHF_FLAG_LITERAL) != 0, mu_out,
                                      mup_out, (cudaStream_t)cuda_stream));
   ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err_rcp, double* max_rel_err_rsqrt) {
+  if (!ctx || !max_rel_err_rcp || !max_rel_err_rsqrt) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  double* d = nullptr;
+  PRHF_CUDA(ctx, cudaMalloc(&d, 2 * sizeof(double)));
+  PRHF_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream));
+  cudaError_t e = prhf::launch_math_selftest(1 << 24, d, ctx->stream);
+  ctx->launches++;
+  double h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, e);
+  *max_rel_err_rcp = h[0];
+  *max_rel_err_rsqrt = h[1];
   return PRHF_OK;
 }
 

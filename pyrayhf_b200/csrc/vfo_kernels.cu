@@ -1,18 +1,21 @@
 // Fused vertical-forward-operator kernels for B200 (sm_100a).
 //
-// One CTA evaluates one tile = (profile, sounding frequency, segment of the stretched grid).
-// Everything the reference materialises as [n_freq x n_points] arrays (lib:410-438 new_alt, dist,
-// den/bmag/bpsi on the grid; lib:500-503 X, Y; ~40 temporaries in lib:209-254) lives in registers;
-// the profile lives in shared memory; HBM sees the inputs once and one double per virtual height.
+// Two launches per call, no [n_freq x n_points] array ever reaches HBM:
 //
-// Stages inside the CTA (reference lines in PyRayHF/library.py):
-//   1. stage den/alt, argmax(den) -> truncation below the peak          lib:371-375
-//   2. node tables (slopes for np.interp, sin/cos of the field angle)    lib:424-426, lib:210-211
-//   3. critical curve X or X+Y at the nodes, running max, validity,
-//      reflection height by np.interp(1.0, ...), back-off 1e-6 km        lib:380-407
-//   4. stretched grid h_i = m_i (h_c - alt0) + alt0, dh_i = h_{i+1}-h_i  lib:413-416
-//   5. interpolate, X, Y, Appleton-Hartree mu', left-Riemann sum         lib:424-426, 500-506, 209-254, 288
-//   6. block reduction, ==0 -> NaN, + min(alt)                           lib:288-292
+//   vfo_rows_kernel  (K1)  one CTA per (profile, 8 sounding frequencies), one warp per frequency:
+//       peak truncation, error status, unmagnetised switch, critical curve X or X+Y at the profile
+//       nodes, running max, validity, reflection height, back-off.          lib:371-407
+//       Output: 8 bytes per (profile, frequency) row (h_c - alt0, NaN = no reflection) and a 32-byte
+//       record per profile.  Rows that do not reflect get their NaN here and cost nothing later.
+//
+//   vfo_tile_kernel  (K2)  one CTA per tile = (profile, frequency, segment of the stretched grid):
+//       stages the profile nodes the tile touches (np.interp slopes, sin/cos of the field angle) in
+//       shared memory, then per grid point: h_i, dh_i (lib:413-416), linear interpolation of
+//       den/bmag/bpsi (lib:424-426), X, Y (lib:500-503), Appleton-Hartree mu' (lib:209-254), the
+//       left-Riemann nansum (lib:288), block reduction, ==0 -> NaN, + min(alt) (lib:290-292).
+//       Everything the reference materialises per grid point lives in registers.
+//
+// PyRayHF/library.py is abbreviated "lib" throughout.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -24,10 +27,13 @@ namespace prhf {
 
 // ------------------------------------------------------------------------------------------
 // stretched-grid multiplier table (lib:314-320): m_i = 1 - (exp(10 (1-u_i)) - 1)/(exp(10) - 1)
+// The table has kMultPad extra entries (value 1) so that the main loop can read m[i+1], m[i+2]
+// unconditionally.
 // ------------------------------------------------------------------------------------------
-__global__ void grid_multiplier_kernel(int n, double step, double* __restrict__ m) {
+__global__ void grid_multiplier_kernel(int n, int n_padded, double step, double* __restrict__ m) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n_padded) return;
+  if (i >= n) { m[i] = 1.0; return; }
   double u = __dmul_rn((double)i, step);        // np.linspace: arange(n) * step ...
   if (i == n - 1 && n > 1) u = 1.0;             // ... with the endpoint forced
   const double fl = __dsub_rn(1.0, u);
@@ -37,12 +43,11 @@ __global__ void grid_multiplier_kernel(int n, double step, double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// block-wide helpers (kThreads = 256 = 8 warps)
+// warp / block helpers (kThreads = 256 = 8 warps)
 // ------------------------------------------------------------------------------------------
 struct BlockScratch {
   double d[kThreads / 32];
   int i[kThreads / 32];
-  double bcast_d[4];
   int bcast_i[4];
 };
 
@@ -104,17 +109,6 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& sc) {
   for (int k = 1; k < kThreads / 32; ++k) r = fmin(r, sc.d[k]);
   return r;
 }
-__device__ __forceinline__ int block_min_i(int v, BlockScratch& sc) {
-  v = warp_min_i(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) sc.i[wid] = v;
-  __syncthreads();
-  int r = sc.i[0];
-#pragma unroll
-  for (int k = 1; k < kThreads / 32; ++k) r = min(r, sc.i[k]);
-  return r;
-}
 
 // np.argmax ordering: NaN wins, then larger value, then first occurrence.
 __device__ __forceinline__ bool arg_precedes(double av, int ai, double bv, int bi) {
@@ -144,127 +138,45 @@ __device__ __forceinline__ int block_argmax(double v, int idx, BlockScratch& sc)
 }
 
 // numpy binary_search_with_guess outcome restricted to [lo, hi]: last j in [lo, hi] with xp[j] <= x,
-// lo - 1 when x < xp[lo].  (The caller guarantees the true bracket lies in [lo - 1, hi].)
+// lo - 1 when x < xp[lo].  STRIDE is in doubles (the node table interleaves 8 doubles per node).
+template <int STRIDE>
 __device__ __forceinline__ int bracket_in(double x, const double* xp, int lo, int hi) {
   int a = lo, b = hi + 1;
   while (a < b) {
     const int mid = a + ((b - a) >> 1);
-    if (x >= xp[mid]) a = mid + 1; else b = mid;
+    if (x >= xp[(ptrdiff_t)mid * STRIDE]) a = mid + 1; else b = mid;
   }
   return a - 1;
 }
 
-struct NodeTables {
-  const double* alt;    // [nt]
-  const double* den;    // [nt]
-  const double* b;      // [nt]
-  const double* psi;    // [nt] degrees
-  const double* sden;   // slopes (last entry 0)
-  const double* sb;
-  const double* spsi;   // degrees / km
-  const double* srad;   // radians / km
-  const double* sn;     // sin(psi_k)
-  const double* cs;     // cos(psi_k)
-};
-
-struct RowConst {
-  double f_hz;      // lib:491
-  double kx;        // cp^2 / f^2     (fast path: X = den * kx)
-  double ky;        // g_p / f        (fast path: Y = b * ky)
-  double alt0;      // aalt[0]
-  double span;      // h_c - aalt[0]  (lib:413)
-  int nt;           // truncated length (= argmax(den))
-  int jlo, jhi;     // node window covered by this tile
-  bool degenerate;  // h_c < alt0: every grid point clamps to node 0
-};
-
-// One tile of grid points [i0, i1); returns this thread's partial nansum of mu' * dh.
-// GENERAL: numpy-literal interpolation + libdevice sincos (needed for non-finite node values or large
-//          per-segment angle steps).  LITERAL: additionally the reference-order Appleton-Hartree.
-template <int MODE, bool GENERAL, bool LITERAL, bool ISO>
-__device__ __forceinline__ double tile_sum(const NodeTables& T, const RowConst& rc, const double* __restrict__ m,
-                                           int i0, int i1, int n_points) {
-  double acc = 0.0;
-  for (int i = i0 + (int)threadIdx.x; i < i1; i += kThreads) {
-    const double mi = __ldg(m + i);
-    const double h = __dadd_rn(__dmul_rn(mi, rc.span), rc.alt0);                 // lib:413
-    double dh;
-    if (i + 1 < n_points) {
-      const double hn = __dadd_rn(__dmul_rn(__ldg(m + i + 1), rc.span), rc.alt0);
-      dh = __dsub_rn(hn, h);                                                     // lib:415
-    } else {
-      dh = kBackoff;                                                             // lib:416
-    }
-    int j = bracket_in(h, T.alt, rc.jlo, rc.jhi);
-    double mup;
-    if (GENERAL || LITERAL) {
-      const double den = interp_numpy(h, j, rc.nt, T.alt, T.den, T.sden);        // lib:424
-      const double b = interp_numpy(h, j, rc.nt, T.alt, T.b, T.sb);              // lib:425
-      const double X = x_literal(den, rc.f_hz);                                  // lib:500
-      if (ISO) {
-        mup = iso_mup(X, nullptr);
-      } else {
-        const double psi = interp_numpy(h, j, rc.nt, T.alt, T.psi, T.spsi);      // lib:426
-        const double Y = y_literal(b, rc.f_hz);                                  // lib:503
-        if (LITERAL) {
-          mup = ah_literal<MODE>(X, Y, psi, nullptr);
-        } else {
-          double sn, cs;
-          sincos(__dmul_rn(psi, kDeg2Rad), &sn, &cs);
-          mup = ah_fast<MODE>(X, Y, sn, cs, nullptr);
-        }
-      }
-    } else {
-      j = max(j, 0);
-      const double t = rc.degenerate ? 0.0 : (h - T.alt[j]);
-      const double X = fma(T.sden[j], t, T.den[j]) * rc.kx;
-      if (ISO) {
-        mup = iso_mup(X, nullptr);
-      } else {
-        const double Y = fma(T.sb[j], t, T.b[j]) * rc.ky;
-        double sn, cs;
-        rotate_sincos(T.sn[j], T.cs[j], T.srad[j] * t, &sn, &cs);
-        mup = ah_fast<MODE>(X, Y, sn, cs, nullptr);
-      }
-    }
-    const double term = mup * dh;                                                // lib:288
-    acc += (term == term) ? term : 0.0;                                          // nansum
-  }
-  return acc;
-}
-
-template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kThreads, 2) vfo_tile_kernel(const VfoParams p) {
+// ==========================================================================================
+// K1: per-row setup
+// ==========================================================================================
+__global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, const int mode) {
   extern __shared__ __align__(16) double smem[];
   __shared__ BlockScratch sc;
   const int A = p.n_alt;
-  double* s_alt = smem;
-  double* s_den = s_alt + A;
-  double* s_b = s_den + A;
-  double* s_psi = s_b + A;
-  double* s_sden = s_psi + A;
-  double* s_sb = s_sden + A;
-  double* s_spsi = s_sb + A;
-  double* s_srad = s_spsi + A;
-  double* s_sn = s_srad + A;
-  double* s_cs = s_sn + A;
-  double* s_crit = s_cs + A;
+  double* s_den = smem;
+  double* s_alt = s_den + A;
+  double* s_b = s_alt + A;
+  double* s_crit = s_b + A;      // [kRowsPerCta][A]
 
-  const int tid = threadIdx.x;
-  const int64_t tile = blockIdx.x;
-  const int seg = (int)(tile % p.n_seg);
-  const int64_t row = tile / p.n_seg;
-  const int r = (int)(row % p.n_freq);
-  const int64_t prof = p.profile_offset + row / p.n_freq;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunks = (p.n_freq + kRowsPerCta - 1) / kRowsPerCta;
+  const int64_t lprof = blockIdx.x / chunks;            // profile index inside this launch
+  const int g = (int)(blockIdx.x % chunks);
+  const int64_t prof = p.profile_offset + lprof;
+  const int r = g * kRowsPerCta + wid;                  // this warp's frequency row
+  const bool has_row = r < p.n_freq;
   const int64_t out_idx = prof * p.n_freq + r;
+  const int64_t lrow = lprof * p.n_freq + r;
 
   const double* g_den = p.den + prof * A;
   const double* g_b = p.bmag + prof * A;
   const double* g_psi = p.bpsi + prof * A;
   const double* g_alt = p.alt + prof * p.alt_stride;
-  const double f_mhz = p.freq[prof * p.freq_stride + r];
 
-  // ---- 1. stage density + altitude, argmax(den) (lib:371), min(alt) (lib:507) ----
+  // ---- stage density + altitude, argmax(den) (lib:371), min(alt) (lib:507) ----
   double best_v = -CUDART_INF;
   int best_i = 0x7fffffff;
   double amin = CUDART_INF;
@@ -279,62 +191,32 @@ __global__ void __launch_bounds__(kThreads, 2) vfo_tile_kernel(const VfoParams p
   const int nt = block_argmax(best_v, best_i, sc);      // truncated length = index of the peak
   const double alt_min = block_min(amin, sc);
 
-  if (nt == 0) {                                         // IndexError in the reference (lib:399)
-    if (seg == 0 && tid == 0) {
-      p.vh[out_idx] = CUDART_NAN;
-      if (r == 0 && p.status) p.status[prof] = 2;
-    }
-    return;
-  }
-
-  // ---- 2. node tables over [0, nt) ----
-  bool neg = false, nonfinite = false, bigstep = false;
+  // ---- node checks over [0, nt): negative density, non-finite values, large angle steps, max|B| ----
+  bool neg = false, general = false;
   double bmax = 0.0;
   for (int k = tid; k < nt; k += kThreads) {
     const double d = s_den[k];
     const double b = g_b[k];
     const double ps = g_psi[k];
     s_b[k] = b;
-    s_psi[k] = ps;
     neg |= (d < 0.0);
-    nonfinite |= !(isfinite(d) && isfinite(b) && isfinite(ps) && isfinite(s_alt[k]));
+    general |= !(isfinite(d) && isfinite(b) && isfinite(ps) && isfinite(s_alt[k]));
     bmax = fmax(bmax, fabs(b));
-    double sn, cs;
-    sincos(ps * kDeg2Rad, &sn, &cs);
-    s_sn[k] = sn;
-    s_cs[k] = cs;
-  }
-  if (__syncthreads_or(neg)) {                           // ValueError in the reference (lib:93-94)
-    if (seg == 0 && tid == 0) {
-      p.vh[out_idx] = CUDART_NAN;
-      if (r == 0 && p.status) p.status[prof] = 1;
+    if (k + 1 < nt) {
+      general |= !(__dsub_rn(s_alt[k + 1], s_alt[k]) > 0.0);
+      general |= !(fabs(__dsub_rn(g_psi[k + 1], ps)) * kDeg2Rad <= kMaxRotateStep);
     }
-    return;
   }
-  for (int k = tid; k < nt; k += kThreads) {
-    double sd = 0.0, sb = 0.0, sp = 0.0;
-    if (k + 1 < nt) {                                    // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
-      const double dx = __dsub_rn(s_alt[k + 1], s_alt[k]);
-      sd = __ddiv_rn(__dsub_rn(s_den[k + 1], s_den[k]), dx);
-      sb = __ddiv_rn(__dsub_rn(s_b[k + 1], s_b[k]), dx);
-      sp = __ddiv_rn(__dsub_rn(s_psi[k + 1], s_psi[k]), dx);
-      nonfinite |= !(dx > 0.0);
-      bigstep |= !(fabs(__dsub_rn(s_psi[k + 1], s_psi[k])) * kDeg2Rad <= kMaxRotateStep);
-    }
-    s_sden[k] = sd;
-    s_sb[k] = sb;
-    s_spsi[k] = sp;
-    s_srad[k] = sp * kDeg2Rad;
-  }
-  const bool general = __syncthreads_or(nonfinite || bigstep);
-  if (seg == 0 && r == 0 && tid == 0 && p.status) p.status[prof] = 0;
+  const bool any_neg = __syncthreads_or(neg);
+  const bool any_general = __syncthreads_or(general);
+  const int status = (nt == 0) ? 2 : (any_neg ? 1 : 0);  // lib:399 IndexError / lib:93-94 ValueError
 
   // Unmagnetised switch (lib:201), decided per profile from the node values: isotropic iff
   // g_p * max|B| / min|f| < 1e-12 over the profile's frequencies.  (The reference takes nanmax|Y|
   // over the regridded [F x N] array of one call; the two differ only for |B| ~ 1e-17 T.)
   bool iso = false;
   bmax = block_max(bmax, sc);
-  if (bmax < 1e-9) {
+  if (status == 0 && bmax < 1e-9) {
     double fmin_abs = CUDART_INF;
     for (int k = tid; k < p.n_freq; k += kThreads) {
       const double f = fabs(__dmul_rn(p.freq[prof * p.freq_stride + k], 1e6));
@@ -344,23 +226,40 @@ __global__ void __launch_bounds__(kThreads, 2) vfo_tile_kernel(const VfoParams p
     iso = (bmax == 0.0) || (__ddiv_rn(__dmul_rn(kGp, bmax), fmin_abs) < kYTol);
   }
 
-  // ---- 3. critical curve at the nodes, validity, reflection height (lib:380-407) ----
-  const double f_hz = __dmul_rn(f_mhz, 1e6);
+  if (g == 0 && tid == 0) {
+    ProfileRecord rec;
+    rec.nt = nt;
+    rec.flags = (iso ? kFlagIso : 0) | (any_general ? kFlagGeneral : 0) | (status ? kFlagFailed : 0);
+    rec.alt_min = alt_min;
+    rec.inv_dalt = (nt > 1) ? (double)(nt - 1) / (s_alt[nt - 1] - s_alt[0]) : 0.0;
+    rec.pad = 0.0;
+    p.prof_rec[lprof] = rec;
+    if (p.status) p.status[prof] = status;
+  }
+  if (!has_row) return;
+  if (status != 0) {
+    if (lane == 0) { p.vh[out_idx] = CUDART_NAN; p.row_span[lrow] = CUDART_NAN; }
+    return;
+  }
+
+  // ---- critical curve at the nodes for this warp's frequency (lib:380-399) ----
+  const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+  double* crit = s_crit + (size_t)wid * A;
   int first_gt = 0x7fffffff;
   bool has_nan = false, any_ge = false;
-  for (int k = tid; k < nt; k += kThreads) {
+  for (int k = lane; k < nt; k += 32) {
     double v = x_literal(s_den[k], f_hz);
-    if (MODE == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
-    s_crit[k] = v;
+    if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+    crit[k] = v;
     has_nan |= isnan(v);
     any_ge |= (v >= 1.0);
     if (v > 1.0) first_gt = min(first_gt, k);
   }
-  const int jstar = block_min_i(first_gt, sc);
-  const bool dead_nan = __syncthreads_or(has_nan);
-  const bool reach = __syncthreads_or(any_ge);
-  if (dead_nan || !reach) {                               // valid == False (lib:399) -> NaN (lib:407)
-    if (seg == 0 && tid == 0) {
+  const int jstar = warp_min_i(first_gt);
+  const bool dead = __any_sync(0xffffffffu, has_nan) || !__any_sync(0xffffffffu, any_ge);
+  __syncwarp();
+  if (dead) {                                             // valid == False (lib:399) -> NaN (lib:407)
+    if (lane == 0) {
       double res = CUDART_NAN;
       if (nt == 1) {
         // numpy's single-node np.interp has no NaN test: interp(NaN, [x0], [f0]) == f0.  A dead row of a
@@ -368,16 +267,22 @@ __global__ void __launch_bounds__(kThreads, 2) vfo_tile_kernel(const VfoParams p
         // 1e-6 (lib:416), and the reference returns alt_min + mu'(node 0) * 1e-6.
         const double X = x_literal(s_den[0], f_hz);
         double mup;
-        if (iso) mup = iso_mup(X, nullptr);
-        else if (LITERAL) mup = ah_literal<MODE>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
-        else mup = ah_fast<MODE>(X, y_literal(s_b[0], f_hz), s_sn[0], s_cs[0], nullptr);
+        if (iso) {
+          mup = iso_mup(X, nullptr);
+        } else if (mode == 0) {
+          mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), g_psi[0], nullptr);
+        } else {
+          mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), g_psi[0], nullptr);
+        }
         const double term = mup * kBackoff;
         if (term == term && term != 0.0) res = term + alt_min;
       }
       p.vh[out_idx] = res;
+      p.row_span[lrow] = CUDART_NAN;
     }
     return;
   }
+  // ---- reflection height: np.interp(1.0, running max, alt) (lib:403-404) ----
   double hcrit;
   if (jstar == 0 || nt == 1) {
     hcrit = s_alt[0];                                     // 1.0 < fcrit[0]: np.interp clamps left
@@ -385,76 +290,267 @@ __global__ void __launch_bounds__(kThreads, 2) vfo_tile_kernel(const VfoParams p
     hcrit = s_alt[nt - 1];                                // running max ends exactly at 1.0
   } else {
     double pm = -CUDART_INF;
-    for (int k = tid; k < jstar; k += kThreads) pm = fmax(pm, s_crit[k]);
-    const double M = block_max(pm, sc);                   // cummax[jstar-1]
+    for (int k = lane; k < jstar; k += 32) pm = fmax(pm, crit[k]);
+    const double M = warp_max(pm);                        // cummax[jstar-1]
     const int j = jstar - 1;
     if (M == 1.0) {
       hcrit = s_alt[j];
     } else {
-      const double slope = __ddiv_rn(__dsub_rn(s_alt[j + 1], s_alt[j]), __dsub_rn(s_crit[jstar], M));
+      const double slope = __ddiv_rn(__dsub_rn(s_alt[j + 1], s_alt[j]), __dsub_rn(crit[jstar], M));
       hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
     }
   }
-  const double hc = __dsub_rn(hcrit, kBackoff);           // lib:407
+  if (lane == 0) {
+    const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
+    p.row_span[lrow] = __dsub_rn(hc, s_alt[0]);           // lib:413 (h_c - aalt[0])
+  }
+}
+
+// ==========================================================================================
+// K2: grid points
+// ==========================================================================================
+// Node table entry in shared memory (one per staged profile level): 64 bytes, read as 4 x LDS.128.
+struct __align__(16) Node {
+  double alt, den;     // level altitude, density
+  double sden, b;      // density slope, field magnitude
+  double sb, srad;     // field slope, field-angle slope in rad/km
+  double sn, cs;       // sin / cos of the field angle at the level
+};
+struct __align__(16) NodeDeg {
+  double psi, spsi;    // field angle in degrees and its slope (numpy-literal / sincos paths)
+};
+
+struct RowConst {
+  double f_hz;      // lib:491
+  double kx;        // cp^2 / f^2     (fast path: X = den * kx)
+  double ky;        // g_p / f        (fast path: Y = b * ky)
+  double alt0;      // aalt[0]
+  double span;      // h_c - aalt[0]  (lib:413)
+  double inv_dalt;  // (nt-1)/(alt[nt-1]-alt[0]): bracket guess for (near-)uniform altitude grids
+  int nt;           // truncated length (= argmax(den))
+  int jlo, jhi;     // node window staged for this tile (absolute indices)
+};
+
+// Bracket of h inside the staged window: last j in [jlo, jhi] with alt[j] <= h (jlo - 1 if below).
+// `guess` is tried first (exact for uniform grids up to rounding), then its neighbours, then bisection.
+__device__ __forceinline__ int find_bracket(double h, const Node* nodes, int jlo, int jhi, int guess) {
+  int j = min(max(guess, jlo), jhi);
+  const double* alt = &nodes[0].alt - (ptrdiff_t)jlo * 8;      // absolute-index view, stride 8 doubles
+  if (h < alt[(ptrdiff_t)j * 8]) {
+    if (j == jlo) return jlo - 1;
+    --j;
+    if (h >= alt[(ptrdiff_t)j * 8]) return j;
+    return bracket_in<8>(h, alt, jlo, j - 1);
+  }
+  if (j == jhi || h < alt[(ptrdiff_t)(j + 1) * 8]) return j;
+  ++j;
+  if (j == jhi || h < alt[(ptrdiff_t)(j + 1) * 8]) return j;
+  return bracket_in<8>(h, alt, j + 1, jhi);
+}
+
+enum : int { kPathFast = 0, kPathGeneral = 1, kPathLiteral = 2 };
+
+// mu' * dh for one grid point (NaN -> 0 handled by the caller).
+template <int MODE, int PATH, bool ISO>
+__device__ __forceinline__ double point_term(double h, double dh, int j, const Node* nodes, const NodeDeg* deg,
+                                             const RowConst& rc) {
+  double mup;
+  if (PATH != kPathFast) {
+    // numpy arr_interp semantics (NaN rescue, exact-node shortcut, clamping) on the staged window
+    const int jj = max(j, rc.jlo) - rc.jlo;
+    double den, b, psi;
+    if (rc.nt == 1 || j < rc.jlo) {
+      den = nodes[0].den; b = nodes[0].b; psi = deg[0].psi;         // left clamp (only when jlo == 0)
+    } else if (j >= rc.nt - 1) {
+      den = nodes[jj].den; b = nodes[jj].b; psi = deg[jj].psi;
+    } else {
+      const Node& n0 = nodes[jj];
+      const Node& n1 = nodes[jj + 1];
+      if (n0.alt == h) {
+        den = n0.den; b = n0.b; psi = deg[jj].psi;
+      } else {
+        const double t = __dsub_rn(h, n0.alt);
+        den = __dadd_rn(__dmul_rn(n0.sden, t), n0.den);
+        b = __dadd_rn(__dmul_rn(n0.sb, t), n0.b);
+        psi = __dadd_rn(__dmul_rn(deg[jj].spsi, t), deg[jj].psi);
+        if (isnan(den) || isnan(b) || isnan(psi)) {
+          const double t1 = __dsub_rn(h, n1.alt);
+          if (isnan(den)) {
+            den = __dadd_rn(__dmul_rn(n0.sden, t1), n1.den);
+            if (isnan(den) && n0.den == n1.den) den = n0.den;
+          }
+          if (isnan(b)) {
+            b = __dadd_rn(__dmul_rn(n0.sb, t1), n1.b);
+            if (isnan(b) && n0.b == n1.b) b = n0.b;
+          }
+          if (isnan(psi)) {
+            psi = __dadd_rn(__dmul_rn(deg[jj].spsi, t1), deg[jj + 1].psi);
+            if (isnan(psi) && deg[jj].psi == deg[jj + 1].psi) psi = deg[jj].psi;
+          }
+        }
+      }
+    }
+    const double X = x_literal(den, rc.f_hz);                        // lib:500
+    if (ISO) {
+      mup = iso_mup(X, nullptr);
+    } else {
+      const double Y = y_literal(b, rc.f_hz);                        // lib:503
+      if (PATH == kPathLiteral) {
+        mup = ah_literal<MODE>(X, Y, psi, nullptr);
+      } else {
+        double sn, cs;
+        sincos(__dmul_rn(psi, kDeg2Rad), &sn, &cs);
+        mup = ah_fast<MODE>(X, Y, sn, cs, nullptr);
+      }
+    }
+  } else {
+    const Node& nd = nodes[max(j, rc.jlo) - rc.jlo];
+    const double t = (j < rc.jlo) ? 0.0 : (h - nd.alt);              // below the first level: clamp (np.interp left)
+    const double X = fma(nd.sden, t, nd.den) * rc.kx;
+    if (ISO) {
+      mup = iso_mup(X, nullptr);
+    } else {
+      const double Y = fma(nd.sb, t, nd.b) * rc.ky;
+      double sn, cs;
+      rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
+      mup = ah_fast<MODE>(X, Y, sn, cs, nullptr);
+    }
+  }
+  return mup * dh;                                                   // lib:288
+}
+
+// Grid points [i0, i1) of one row, two adjacent points per thread per iteration.
+template <int MODE, int PATH, bool ISO>
+__device__ __forceinline__ double tile_sum(const Node* nodes, const NodeDeg* deg, const RowConst& rc,
+                                           const double* __restrict__ m, int i0, int i1, int n_points) {
+  double acc0 = 0.0, acc1 = 0.0;
+  const double2* m2 = reinterpret_cast<const double2*>(m);
+  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kThreads) {
+    const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
+    const double mn = __ldg(m + i + 2);
+    const double h0 = __dadd_rn(__dmul_rn(mm.x, rc.span), rc.alt0);  // lib:413
+    const double h1 = __dadd_rn(__dmul_rn(mm.y, rc.span), rc.alt0);
+    const double h2 = __dadd_rn(__dmul_rn(mn, rc.span), rc.alt0);
+    const double dh0 = (i == n_points - 1) ? kBackoff : __dsub_rn(h1, h0);      // lib:415-416
+    const double dh1 = (i + 1 == n_points - 1) ? kBackoff : __dsub_rn(h2, h1);
+    const int g0 = __double2int_rd((h0 - rc.alt0) * rc.inv_dalt);
+    const int j0 = find_bracket(h0, nodes, rc.jlo, rc.jhi, g0);
+    const int j1 = find_bracket(h1, nodes, rc.jlo, rc.jhi, j0);
+    const double t0 = point_term<MODE, PATH, ISO>(h0, dh0, j0, nodes, deg, rc);
+    const double t1 = point_term<MODE, PATH, ISO>(h1, dh1, j1, nodes, deg, rc);
+    acc0 += (t0 == t0) ? t0 : 0.0;                                   // nansum
+    acc1 += (t1 == t1 && i + 1 < i1) ? t1 : 0.0;
+  }
+  return acc0 + acc1;
+}
+
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int seg = (int)(tile % p.n_seg);
+  const int64_t lrow = tile / p.n_seg;                    // row index inside this launch
+  const double span = p.row_span[lrow];
+  if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
+
+  const int r = (int)(lrow % p.n_freq);
+  const int64_t lprof = lrow / p.n_freq;
+  const int64_t prof = p.profile_offset + lprof;
+  const ProfileRecord rec = p.prof_rec[lprof];
+  const int nt = rec.nt;
+  const bool iso = (rec.flags & kFlagIso) != 0;
+  const bool general = (rec.flags & kFlagGeneral) != 0;
+
+  const int A = p.n_alt;
+  const double* g_den = p.den + prof * A;
+  const double* g_b = p.bmag + prof * A;
+  const double* g_psi = p.bpsi + prof * A;
+  const double* g_alt = p.alt + prof * p.alt_stride;
 
   RowConst rc;
-  rc.f_hz = f_hz;
-  rc.kx = (kCp * kCp) / (f_hz * f_hz);
-  rc.ky = kGp / f_hz;
-  rc.alt0 = s_alt[0];
-  rc.span = __dsub_rn(hc, s_alt[0]);
+  rc.f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);
+  rc.kx = (kCp * kCp) / (rc.f_hz * rc.f_hz);
+  rc.ky = kGp / rc.f_hz;
+  rc.alt0 = g_alt[0];
+  rc.span = span;
+  rc.inv_dalt = rec.inv_dalt;
   rc.nt = nt;
-  rc.degenerate = (hc < s_alt[0]) || (nt == 1);
 
-  // ---- 4. node window of this tile ----
+  // ---- node window of this tile ----
   const int i0 = seg * p.seg_len;
   const int i1 = min(p.n_points, i0 + p.seg_len);
-  __syncthreads();
   if (tid == 0 || tid == 32) {
-    const int i = (tid == 0) ? i0 : (i1 - 1);
-    const double h = __dadd_rn(__dmul_rn(__ldg(p.mult + i), rc.span), rc.alt0);
-    sc.bcast_i[tid >> 5] = bracket_in(h, s_alt, 0, nt - 1);
+    int j = 0;
+    if (span > 0.0 && nt > 1) {                           // span <= 0: every point clamps to node 0
+      const int i = (tid == 0) ? i0 : (i1 - 1);
+      const double h = __dadd_rn(__dmul_rn(__ldg(p.mult + i), span), rc.alt0);
+      // guess from the mean spacing, verify against the global altitude table, bisect if needed
+      const int gj = min(max(__double2int_rd((h - rc.alt0) * rec.inv_dalt), 0), nt - 1);
+      if (h >= g_alt[gj] && (gj == nt - 1 || h < g_alt[gj + 1])) j = gj;
+      else j = max(bracket_in<1>(h, g_alt, 0, nt - 1), 0);
+    }
+    sc.bcast_i[tid >> 5] = j;
   }
   __syncthreads();
-  {
-    const int ja = sc.bcast_i[0], jb = sc.bcast_i[1];
-    rc.jlo = max(min(ja, jb), 0);
-    rc.jhi = max(max(ja, jb), 0);
+  rc.jlo = min(sc.bcast_i[0], sc.bcast_i[1]);
+  rc.jhi = max(sc.bcast_i[0], sc.bcast_i[1]);
+  const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
+
+  Node* nodes = reinterpret_cast<Node*>(smem_raw);
+  NodeDeg* deg = reinterpret_cast<NodeDeg*>(smem_raw + sizeof(Node) * (size_t)A);
+  for (int q = tid; q < n_stage; q += kThreads) {
+    const int k = rc.jlo + q;
+    const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
+    double sd = 0.0, sb = 0.0, sp = 0.0;
+    if (k + 1 < nt) {                                     // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
+      const double dx = __dsub_rn(g_alt[k + 1], a0);
+      sd = __ddiv_rn(__dsub_rn(g_den[k + 1], d0), dx);
+      sb = __ddiv_rn(__dsub_rn(g_b[k + 1], b0), dx);
+      sp = __ddiv_rn(__dsub_rn(g_psi[k + 1], p0), dx);
+    }
+    double sn, cs;
+    sincos(p0 * kDeg2Rad, &sn, &cs);
+    Node nd;
+    nd.alt = a0; nd.den = d0; nd.sden = sd; nd.b = b0; nd.sb = sb; nd.srad = sp * kDeg2Rad; nd.sn = sn; nd.cs = cs;
+    nodes[q] = nd;
+    NodeDeg dg;
+    dg.psi = p0; dg.spsi = sp;
+    deg[q] = dg;
   }
+  __syncthreads();
 
-  NodeTables T{s_alt, s_den, s_b, s_psi, s_sden, s_sb, s_spsi, s_srad, s_sn, s_cs};
-
-  // ---- 5. grid points of the tile ----
+  // ---- grid points of the tile ----
   double acc;
   if (LITERAL) {
-    acc = iso ? tile_sum<MODE, true, true, true>(T, rc, p.mult, i0, i1, p.n_points)
-              : tile_sum<MODE, true, true, false>(T, rc, p.mult, i0, i1, p.n_points);
+    acc = iso ? tile_sum<MODE, kPathLiteral, true>(nodes, deg, rc, p.mult, i0, i1, p.n_points)
+              : tile_sum<MODE, kPathLiteral, false>(nodes, deg, rc, p.mult, i0, i1, p.n_points);
   } else if (iso) {
-    acc = tile_sum<MODE, true, false, true>(T, rc, p.mult, i0, i1, p.n_points);
+    acc = tile_sum<MODE, kPathGeneral, true>(nodes, deg, rc, p.mult, i0, i1, p.n_points);
   } else if (general) {
-    acc = tile_sum<MODE, true, false, false>(T, rc, p.mult, i0, i1, p.n_points);
+    acc = tile_sum<MODE, kPathGeneral, false>(nodes, deg, rc, p.mult, i0, i1, p.n_points);
   } else {
-    acc = tile_sum<MODE, false, false, false>(T, rc, p.mult, i0, i1, p.n_points);
+    acc = tile_sum<MODE, kPathFast, false>(nodes, deg, rc, p.mult, i0, i1, p.n_points);
   }
 
-  // ---- 6. reduce, finish (lib:288-292) ----
+  // ---- reduce, finish (lib:288-292) ----
   const double s_tile = block_sum(acc, sc);
   if (tid != 0) return;
   double total = s_tile;
   if (p.n_seg > 1) {
-    const int64_t local_row = row;                        // row index inside this launch
-    double* part = p.partial + local_row * p.n_seg;
+    double* part = p.partial + lrow * p.n_seg;
     __stcg(part + seg, s_tile);
     __threadfence();
-    const unsigned prev = atomicAdd(p.counter + local_row, 1u);
+    const unsigned prev = atomicAdd(p.counter + lrow, 1u);
     if (prev != (unsigned)(p.n_seg - 1)) return;
     __threadfence();
     total = 0.0;
     for (int s = 0; s < p.n_seg; ++s) total += __ldcg(part + s);   // fixed order: deterministic
-    p.counter[local_row] = 0u;                            // self-reset for the next launch
+    p.counter[lrow] = 0u;                                 // self-reset for the next launch
   }
   if (total == 0.0) total = CUDART_NAN;                   // lib:290
-  p.vh[out_idx] = total + alt_min;                        // lib:292
+  p.vh[prof * p.n_freq + r] = total + rec.alt_min;        // lib:292
 }
 
 // ------------------------------------------------------------------------------------------
@@ -495,14 +591,47 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters,
   if (s == 123.456) out[0] = s;   // never true; keeps the chain alive
 }
 
+// accuracy self-test of the fast reciprocal / reciprocal square root (max relative error vs IEEE)
+__global__ void math_selftest_kernel(int n, double* __restrict__ err) {
+  double e_rcp = 0.0, e_rsq = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // log-uniform samples in [1e-30, 1e30] interleaved with a dense sweep of one binade
+    const double u = (double)i / (double)n;
+    const double x = (i & 1) ? exp(138.0 * (u - 0.5)) : 1.0 + u;
+    e_rcp = fmax(e_rcp, fabs(rcp_fast(x) - __drcp_rn(x)) * x);
+    const double rs = __drcp_rn(__dsqrt_rn(x));
+    e_rsq = fmax(e_rsq, fabs(rsqrt_fast(x) - rs) / rs);
+  }
+  e_rcp = warp_max(e_rcp);
+  e_rsq = warp_max(e_rsq);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned long long*>(err), (unsigned long long)__double_as_longlong(e_rcp));
+    atomicMax(reinterpret_cast<unsigned long long*>(err + 1), (unsigned long long)__double_as_longlong(e_rsq));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-size_t vfo_smem_bytes(int n_alt) { return sizeof(double) * 11 * (size_t)n_alt; }
+size_t vfo_rows_smem_bytes(int n_alt) { return sizeof(double) * (3 + kRowsPerCta) * (size_t)n_alt; }
+size_t vfo_tile_smem_bytes(int n_alt) { return (sizeof(Node) + sizeof(NodeDeg)) * (size_t)n_alt; }
+size_t vfo_smem_bytes(int n_alt) {
+  const size_t a = vfo_rows_smem_bytes(n_alt), b = vfo_tile_smem_bytes(n_alt);
+  return a > b ? a : b;
+}
+
+cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream) {
+  const size_t smem = vfo_rows_smem_bytes(p.n_alt);
+  cudaError_t e = cudaFuncSetAttribute(vfo_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int chunks = (p.n_freq + kRowsPerCta - 1) / kRowsPerCta;
+  vfo_rows_kernel<<<(unsigned)(n_profiles * chunks), kThreads, smem, stream>>>(p, mode);
+  return cudaGetLastError();
+}
 
 template <int MODE, bool LITERAL>
 static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
-  const size_t smem = vfo_smem_bytes(p.n_alt);
+  const size_t smem = vfo_tile_smem_bytes(p.n_alt);
   auto kern = vfo_tile_kernel<MODE, LITERAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -517,7 +646,8 @@ cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t
 
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream) {
   const double step = (n > 1) ? 1.0 / (double)(n - 1) : 0.0;
-  grid_multiplier_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, step, m);
+  const int np = n + kMultPad;
+  grid_multiplier_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, step, m);
   return cudaGetLastError();
 }
 
@@ -539,6 +669,11 @@ cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, i
 
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream) {
   dfma_probe_kernel<<<blocks, 256, 0, stream>>>(out, iters, 1.0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_math_selftest(int n, double* err2, cudaStream_t stream) {
+  math_selftest_kernel<<<148 * 4, 256, 0, stream>>>(n, err2);
   return cudaGetLastError();
 }
 

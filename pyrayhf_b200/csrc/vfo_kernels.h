@@ -7,6 +7,20 @@
 namespace prhf {
 
 constexpr int kThreads = 256;
+constexpr int kRowsPerCta = kThreads / 32;   // K1: one warp per sounding frequency
+constexpr int kMultPad = 4;                  // extra multiplier-table entries (value 1) past n_points
+
+constexpr int kFlagIso = 1;       // unmagnetised branch (lib:201)
+constexpr int kFlagGeneral = 2;   // non-finite node values / non-increasing altitudes / large angle steps
+constexpr int kFlagFailed = 4;    // status != 0
+
+struct ProfileRecord {            // 32 bytes per profile, written by K1, read by K2
+  int nt;                         // truncated length = argmax(den) (lib:371)
+  int flags;
+  double alt_min;                 // np.min(alt) (lib:507)
+  double inv_dalt;                // (nt-1)/(alt[nt-1]-alt[0]); bracket guess for near-uniform grids
+  double pad;
+};
 
 struct VfoParams {
   const double* freq;      // MHz; [n_freq] or per-profile rows
@@ -19,21 +33,25 @@ struct VfoParams {
   int64_t alt_stride;      // 0 = shared
   int n_alt;
   int64_t profile_offset;  // first profile handled by this launch
-  const double* mult;      // stretched-grid multiplier [n_points]
+  const double* mult;      // stretched-grid multiplier [n_points + kMultPad]
   int n_points;
-  int seg_len;             // grid points per tile
+  int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null
+  ProfileRecord* prof_rec; // [profiles_in_launch]
+  double* row_span;        // [rows_in_launch]  h_c - alt0, NaN = row finished by K1
   double* partial;         // [rows_in_launch x n_seg] when n_seg > 1
   unsigned* counter;       // [rows_in_launch], zero on entry, zero on exit
 };
 
 size_t vfo_smem_bytes(int n_alt);
+cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
+cudaError_t launch_math_selftest(int n, double* err2, cudaStream_t stream);
 
 }  // namespace prhf

@@ -211,3 +211,11 @@ def test_full_size_properties(vfo):
     for p in (0, 63):
         ref = vfo_oracle.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, 'X', 20000)
         assert np.array_equal(np.isnan(a[p]), np.isnan(ref)) and rel_err(a[p], ref) < 1e-9
+
+
+def test_fast_math_accuracy(vfo):
+    """rcp_fast / rsqrt_fast (MUFU seed + refinement) against IEEE division and sqrt."""
+    from pyrayhf_b200 import _cabi
+    e_rcp, e_rsqrt = _cabi.context(0).selftest_math()
+    assert 0.0 <= e_rcp < 4.5e-16, e_rcp
+    assert 0.0 <= e_rsqrt < 4.5e-16, e_rsqrt
