@@ -113,8 +113,10 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
 int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out);
 
 /* Accuracy self-test of the kernel's fast reciprocal / reciprocal-square-root primitives: maximum
- * relative error against IEEE division / sqrt over 2^24 samples (log-uniform 1e-30..1e30 and one binade). */
-int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err_rcp, double* max_rel_err_rsqrt);
+ * relative error against IEEE division / sqrt over 2^24 samples (log-uniform 1e-30..1e30 and one binade).
+ * out[0] rcp_fast, out[1] rsqrt_fast, out[2] raw MUFU.RCP64H seed, out[3] raw MUFU.RSQ64H seed,
+ * out[4] / out[5] the seeds after one cubically convergent step. */
+int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err6);
 
 /* Number of kernel launches issued through this ctx since creation (for bench accounting). */
 int64_t prhf_launch_count(const prhf_ctx* ctx);

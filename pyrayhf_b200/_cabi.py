@@ -79,7 +79,7 @@ def load():
         L.prhf_mu_mup_f64.restype = _i
         L.prhf_measure_fp64_peak.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
         L.prhf_measure_fp64_peak.restype = _i
-        L.prhf_selftest_math.argtypes = [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.prhf_selftest_math.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
         L.prhf_selftest_math.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
@@ -138,9 +138,9 @@ class Context:
         return self._L.prhf_launch_count(self._h)
 
     def selftest_math(self):
-        a, b = ctypes.c_double(), ctypes.c_double()
-        self.check(self._L.prhf_selftest_math(self._h, ctypes.byref(a), ctypes.byref(b)))
-        return a.value, b.value
+        out = (ctypes.c_double * 6)()
+        self.check(self._L.prhf_selftest_math(self._h, out))
+        return list(out)
 
     def measure_fp64_peak(self):
         out = ctypes.c_double()

@@ -393,21 +393,20 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
   return PRHF_OK;
 }
 
-int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err_rcp, double* max_rel_err_rsqrt) {
-  if (!ctx || !max_rel_err_rcp || !max_rel_err_rsqrt) return PRHF_ERR_INVALID_ARG;
+int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err6) {
+  if (!ctx || !max_rel_err6) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   double* d = nullptr;
-  PRHF_CUDA(ctx, cudaMalloc(&d, 2 * sizeof(double)));
-  PRHF_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream));
+  PRHF_CUDA(ctx, cudaMalloc(&d, 6 * sizeof(double)));
+  PRHF_CUDA(ctx, cudaMemsetAsync(d, 0, 6 * sizeof(double), ctx->stream));
   cudaError_t e = prhf::launch_math_selftest(1 << 24, d, ctx->stream);
   ctx->launches++;
-  double h[2] = {0, 0};
+  double h[6] = {0, 0, 0, 0, 0, 0};
   if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
   if (e != cudaSuccess) return fail(ctx, e);
-  *max_rel_err_rcp = h[0];
-  *max_rel_err_rsqrt = h[1];
+  for (int k = 0; k < 6; ++k) max_rel_err6[k] = h[k];
   return PRHF_OK;
 }
 

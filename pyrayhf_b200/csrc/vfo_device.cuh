@@ -89,26 +89,23 @@ __device__ __forceinline__ double iso_mup(double X, double* mu_out) {
 }
 
 // ---- reciprocal and reciprocal square root without the libdevice special-case paths ----
-// MUFU.RCP64H / MUFU.RSQ64H seed (rcp/rsqrt.approx.ftz.f64) + one cubically convergent step + one Newton
-// step: 5 (rcp) / 9 (rsqrt) FP64 instructions, no branches.  Max relative error measured on B200 by
-// prhf_selftest_math (tests/test_gpu_parity.py::test_fast_math_accuracy): ~1 ulp.  Zero, negative,
-// infinite and denormal inputs yield NaN/inf instead of the IEEE special values; on this path they only
-// occur at points whose term the reference drops as NaN anyway (lib:233, lib:288).
+// MUFU.RCP64H / MUFU.RSQ64H seed (rcp/rsqrt.approx.ftz.f64, measured max relative error 9.9e-7 / 9.2e-7
+// on B200) followed by ONE cubically convergent step: 3 (rcp) / 5 (rsqrt) FP64 instructions, no branches.
+// Measured max relative error against IEEE division / sqrt (prhf_selftest_math, 2^24 samples over
+// 1e-30..1e30): 2.2e-16 / 2.7e-16.  Zero, negative, infinite and denormal inputs yield NaN/inf rather than
+// the IEEE special values; on this path they only occur at points whose term the reference drops as NaN
+// anyway (lib:233, lib:288).
 __device__ __forceinline__ double rcp_fast(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, fma(e, e, e), y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);                      // y (1 + e + e^2)
 }
 __device__ __forceinline__ double rsqrt_fast(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-(x * y), y, 1.0);
-  y = fma(y, e * fma(e, 0.375, 0.5), y);
-  e = fma(-(x * y), y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-(x * y), y, 1.0);              // 1 - x y^2
+  return fma(y, e * fma(e, 0.375, 0.5), y);            // y (1 + e/2 + 3 e^2 / 8)
 }
 
 // ---- restructured Appleton-Hartree: same formulas as lib:209-254, algebraically rearranged ----
@@ -156,6 +153,55 @@ __device__ __forceinline__ double ah_fast(double X, double Y, double sn, double 
   return mup;
 }
 
+// ---- the same formulas with the reciprocal folded into the second reciprocal square root ----
+// Used for every grid point of a row that reflects above the first level (the hot loop).
+//   X-mode:  E = D - X Xm1 (= D mu^2), rs = 1/sqrt(D E):  mu = |E rs|, 1/D = (E rs) rs,
+//            1/(D mu) = copysign(rs, E rs)           -- exact for either sign of D
+//   O-mode:  N = Xm1 P + w, G = P + w, mu^2 = N/G, rs = 1/sqrt(Xm1^2 N G):  mu = Xm1 N rs,
+//            1/G = (Xm1 N rs)(Xm1 rs), q = X P / G, 1/(D mu) = P rs   -- assumes Xm1 > 0, which holds at
+//            every grid point below the X = 1 reflection level (rows that start above it take ah_fast)
+// 41 (X) / 42 (O) FP64 instructions per point including both reciprocal square roots.
+template <int MODE>
+__device__ __forceinline__ double ah_core(double X, double Y, double sn, double cs) {
+  const double YT = Y * sn, YL = Y * cs;
+  const double Xm1 = 1.0 - X;
+  const double a = 0.5 * (YT * YT);
+  const double w = (YL * YL) * Xm1;
+  const double a2 = a * a;
+  const double alpha = fma(w, Xm1, a2);
+  const double rb = rsqrt_fast(alpha);
+  const double beta = alpha * rb;
+  const double P = a + beta;
+  const double two_a = a + a;
+  double mu, c, q, dDdX, YdDdY;
+  if (MODE == 1) {
+    const double D = Xm1 - P;
+    const double XX = X * Xm1;
+    const double E = D - XX;
+    const double rs = rsqrt_fast(D * E);
+    const double t1 = E * rs;
+    mu = fabs(t1);
+    q = XX * (t1 * rs);
+    c = copysign(rs, t1);
+    dDdX = fma(w, rb, -1.0);
+    YdDdY = -fma(a2, rb, beta) - two_a;
+  } else {
+    const double N = fma(Xm1, P, w);
+    const double G = P + w;
+    const double z = Xm1 * N;
+    const double rs = rsqrt_fast(z * (Xm1 * G));
+    const double v = z * rs;
+    mu = fabs(v);
+    q = (X * P) * (v * (Xm1 * rs));
+    c = P * rs;
+    dDdX = -fma(w, rb, 1.0);
+    YdDdY = fma(a2, rb, beta) - two_a;
+  }
+  const double br = fma(0.5 * q, YdDdY, X * fma(q, dDdX, fma(2.0, X, -1.0)));
+  const double mup = fma(-c, br, mu);
+  return (mu <= 1.0) ? mup : CUDART_NAN;               // lib:233 (NaN mu) and lib:238
+}
+
 // sin/cos of (r_k + delta) from the node's sin/cos and a short Taylor series in delta (|delta| <= 0.05:
 // truncation < 6e-18).  Replaces a full-range sincos per grid point.
 __device__ __forceinline__ void rotate_sincos(double sk, double ck, double delta, double* sn, double* cs) {
@@ -172,5 +218,12 @@ __device__ __forceinline__ void rotate_sincos(double sk, double ck, double delta
   *cs = fma(-sk, sd, fma(ck, cdm1, ck));
 }
 constexpr double kMaxRotateStep = 0.05;               // rad; larger per-segment steps use sincos()
+// Second-order version for |delta| <= 4e-4 rad (0.023 deg per profile level; truncation delta^3/6 < 1.1e-11).
+__device__ __forceinline__ void rotate_sincos_small(double sk, double ck, double delta, double* sn, double* cs) {
+  const double e2 = (-0.5 * delta) * delta;
+  *sn = fma(sk, e2, fma(delta, ck, sk));
+  *cs = fma(ck, e2, fma(-delta, sk, ck));
+}
+constexpr double kSmallRotateStep = 4e-4;
 
 }  // namespace prhf

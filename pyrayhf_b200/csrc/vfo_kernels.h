@@ -13,6 +13,8 @@ constexpr int kMultPad = 4;                  // extra multiplier-table entries (
 constexpr int kFlagIso = 1;       // unmagnetised branch (lib:201)
 constexpr int kFlagGeneral = 2;   // non-finite node values / non-increasing altitudes / large angle steps
 constexpr int kFlagFailed = 4;    // status != 0
+constexpr int kFlagPsiConst = 8;  // field angle identical at every level below the peak
+constexpr int kFlagPsiSmall = 16; // per-level field-angle steps <= kSmallRotateStep
 
 struct ProfileRecord {            // 32 bytes per profile, written by K1, read by K2
   int nt;                         // truncated length = argmax(den) (lib:371)
