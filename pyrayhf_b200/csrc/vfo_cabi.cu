@@ -41,6 +41,7 @@ struct prhf_ctx {
   int64_t launches = 0;
   int seg_len_override = 0;          // PRHF_SEG_LEN (tuning / tests)
   int64_t target_tiles = 0;          // PRHF_TARGET_TILES
+  long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
 };
 
 namespace {
@@ -237,6 +238,24 @@ int prhf_max_n_alt(const prhf_ctx* ctx) {
 
 int64_t prhf_launch_count(const prhf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+#ifdef PRHF_TRACE
+// developer-only: allocate / read back the tile-kernel phase trace (not declared in the public header)
+int prhf_debug_trace_alloc(prhf_ctx* ctx, int64_t n_tiles) {
+  DeviceGuard g(ctx->device);
+  if (ctx->trace) cudaFree(ctx->trace);
+  ctx->trace = nullptr;
+  PRHF_CUDA(ctx, cudaMalloc(&ctx->trace, sizeof(long long) * 8 * (size_t)n_tiles));
+  PRHF_CUDA(ctx, cudaMemset(ctx->trace, 0, sizeof(long long) * 8 * (size_t)n_tiles));
+  return PRHF_OK;
+}
+int prhf_debug_trace_read(prhf_ctx* ctx, int64_t n_tiles, long long* out) {
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, cudaDeviceSynchronize());
+  PRHF_CUDA(ctx, cudaMemcpy(out, ctx->trace, sizeof(long long) * 8 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+  return PRHF_OK;
+}
+#endif
+
 int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* cuda_stream) {
   if (!ctx || n_points < 1 || !m_out) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
@@ -277,6 +296,14 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     rc = ensure_workspace(ctx, (size_t)rows_launch * n_seg, (size_t)rows_launch);
     if (rc != PRHF_OK) return rc;
   }
+  // K1 granularity: 8 rows per CTA while the launch is small (latency matters), whole profiles per CTA
+  // once there are enough profiles to fill the GPU (amortises the per-CTA profile staging).
+  const int chunks8 = (n_freq + prhf::kRowsPerCta - 1) / prhf::kRowsPerCta;
+  int rows_per_warp = 1;
+  if (n_profiles * chunks8 > (int64_t)ctx->sm_count * 64) {
+    rows_per_warp = (int)std::min<int64_t>(chunks8, (n_profiles * chunks8) / ((int64_t)ctx->sm_count * 32));
+    rows_per_warp = std::max(rows_per_warp, 1);
+  }
   for (int64_t p0 = 0; p0 < n_profiles; p0 += prof_per_launch) {
     const int64_t np = std::min(prof_per_launch, n_profiles - p0);
     prhf::VfoParams P;
@@ -294,12 +321,14 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_points = n_points;
     P.seg_len = seg_len;
     P.n_seg = n_seg;
+    P.rows_per_warp = rows_per_warp;
     P.vh = vh_out;
     P.status = status;
     P.prof_rec = ctx->prof_rec;
     P.row_span = ctx->row_span;
     P.partial = ctx->partial;
     P.counter = ctx->counter;
+    P.trace = ctx->trace;
     PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
     PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, (flags & PRHF_FLAG_LITERAL) != 0, np * tiles_per_profile, stream));
     ctx->launches += 2;

@@ -19,6 +19,7 @@ constexpr double kSharp = 10.0;             // lib:363
 constexpr double kBackoff = 1e-6;           // lib:378 (the dh argument is overwritten)
 constexpr double kYTol = 1e-12;             // lib:163
 constexpr double kDeg2Rad = 0.017453292519943295;  // fl(pi/180): np.deg2rad(x) == x * (pi/180)
+constexpr double kScreenTol = 6e-15;        // K1 node screening: > 4x the 13-ulp bound on |screen - literal| / (|X|+|Y|)
 
 // ---- lib:136 and lib:157 with the reference's rounding order (no contraction) ----
 __device__ __forceinline__ double x_literal(double den, double f_hz) {

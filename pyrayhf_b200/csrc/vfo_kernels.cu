@@ -25,6 +25,27 @@
 
 namespace prhf {
 
+// Optional per-CTA phase trace (developer builds only: make TRACE=1).  Thread 0 of every tile-kernel CTA
+// stores {smid, globaltimer at entry, clock64 at 6 phase boundaries} into p.trace.
+#ifdef PRHF_TRACE
+#define PRHF_TRACE_MARK(slot)                                                              \
+  do {                                                                                     \
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); \
+  } while (0)
+__device__ __forceinline__ long long trace_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int trace_smid() {
+  int s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
+}
+#else
+#define PRHF_TRACE_MARK(slot) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // stretched-grid multiplier table (lib:314-320): m_i = 1 - (exp(10 (1-u_i)) - 1)/(exp(10) - 1)
 // The table has kMultPad extra entries (value 1) so that the main loop can read m[i+1], m[i+2]
@@ -159,58 +180,64 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
   double* s_den = smem;
   double* s_alt = s_den + A;
   double* s_b = s_alt + A;
-  double* s_crit = s_b + A;      // [kRowsPerCta][A]
+  double* s_psi = s_b + A;
+  double* s_crit = s_psi + A;    // [kRowsPerCta][A]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int chunks = (p.n_freq + kRowsPerCta - 1) / kRowsPerCta;
+  const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
+  const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   const int64_t lprof = blockIdx.x / chunks;            // profile index inside this launch
   const int g = (int)(blockIdx.x % chunks);
   const int64_t prof = p.profile_offset + lprof;
-  const int r = g * kRowsPerCta + wid;                  // this warp's frequency row
-  const bool has_row = r < p.n_freq;
-  const int64_t out_idx = prof * p.n_freq + r;
-  const int64_t lrow = lprof * p.n_freq + r;
 
   const double* g_den = p.den + prof * A;
   const double* g_b = p.bmag + prof * A;
   const double* g_psi = p.bpsi + prof * A;
   const double* g_alt = p.alt + prof * p.alt_stride;
 
-  // ---- stage density + altitude, argmax(den) (lib:371), min(alt) (lib:507) ----
+  // ---- stage the whole profile with all loads in flight at once (one DRAM latency), then
+  //      argmax(den) (lib:371) and min(alt) (lib:507) ----
   double best_v = -CUDART_INF;
   int best_i = 0x7fffffff;
   double amin = CUDART_INF;
   for (int k = tid; k < A; k += kThreads) {
     const double d = g_den[k];
     const double a = g_alt[k];
+    const double b = g_b[k];
+    const double ps = g_psi[k];
     s_den[k] = d;
     s_alt[k] = a;
+    s_b[k] = b;
+    s_psi[k] = ps;
     if (arg_precedes(d, k, best_v, best_i)) { best_v = d; best_i = k; }
     amin = fmin(amin, a);
   }
-  const int nt = block_argmax(best_v, best_i, sc);      // truncated length = index of the peak
+  const int nt = block_argmax(best_v, best_i, sc);      // truncated length = index of the peak (syncs)
   const double alt_min = block_min(amin, sc);
 
-  // ---- node checks over [0, nt): negative density, non-finite values, large angle steps, max|B| ----
-  bool neg = false, general = false;
+  // ---- node checks over [0, nt): negative density, non-finite values, angle steps, grid uniformity, max|B| ----
+  bool neg = false, general = false, nonuniform = false;
   double bmax = 0.0, step_max = 0.0;
+  const double alt0 = s_alt[0];
+  const double mean_step = (nt > 1) ? (s_alt[nt - 1] - alt0) / (double)(nt - 1) : 1.0;
   for (int k = tid; k < nt; k += kThreads) {
     const double d = s_den[k];
-    const double b = g_b[k];
-    const double ps = g_psi[k];
-    s_b[k] = b;
+    const double b = s_b[k];
+    const double ps = s_psi[k];
     neg |= (d < 0.0);
     general |= !(isfinite(d) && isfinite(b) && isfinite(ps) && isfinite(s_alt[k]));
     bmax = fmax(bmax, fabs(b));
+    nonuniform |= !(fabs(s_alt[k] - fma((double)k, mean_step, alt0)) <= 0.25 * mean_step);
     if (k + 1 < nt) {
       general |= !(__dsub_rn(s_alt[k + 1], s_alt[k]) > 0.0);
-      const double step = fabs(__dsub_rn(g_psi[k + 1], ps)) * kDeg2Rad;
+      const double step = fabs(__dsub_rn(s_psi[k + 1], ps)) * kDeg2Rad;
       general |= !(step <= kMaxRotateStep);
       step_max = fmax(step_max, step);
     }
   }
   const bool any_neg = __syncthreads_or(neg);
   const bool any_general = __syncthreads_or(general);
+  const bool any_nonuniform = __syncthreads_or(nonuniform);
   const int status = (nt == 0) ? 2 : (any_neg ? 1 : 0);  // lib:399 IndexError / lib:93-94 ValueError
 
   // Unmagnetised switch (lib:201), decided per profile from the node values: isotropic iff
@@ -233,80 +260,146 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     ProfileRecord rec;
     rec.nt = nt;
     rec.flags = (iso ? kFlagIso : 0) | (any_general ? kFlagGeneral : 0) | (status ? kFlagFailed : 0) |
-                (step_max == 0.0 ? kFlagPsiConst : 0) | (step_max <= kSmallRotateStep ? kFlagPsiSmall : 0);
+                (step_max == 0.0 ? kFlagPsiConst : 0) | (step_max <= kSmallRotateStep ? kFlagPsiSmall : 0) |
+                (any_nonuniform ? 0 : kFlagUniformAlt);
     rec.alt_min = alt_min;
-    rec.inv_dalt = (nt > 1) ? (double)(nt - 1) / (s_alt[nt - 1] - s_alt[0]) : 0.0;
-    rec.pad = 0.0;
+    rec.inv_dalt = (nt > 1) ? (double)(nt - 1) / (s_alt[nt - 1] - alt0) : 0.0;
+    rec.alt0 = alt0;
+    sincos(s_psi[0] * kDeg2Rad, &rec.sn0, &rec.cs0);
+    rec.pad[0] = rec.pad[1] = 0.0;
     p.prof_rec[lprof] = rec;
     if (p.status) p.status[prof] = status;
   }
-  if (!has_row) return;
-  if (status != 0) {
-    if (lane == 0) { p.vh[out_idx] = CUDART_NAN; p.row_span[lrow] = CUDART_NAN; }
-    return;
-  }
-
-  // ---- critical curve at the nodes for this warp's frequency (lib:380-399) ----
-  const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+  // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
   double* crit = s_crit + (size_t)wid * A;
-  int first_gt = 0x7fffffff;
-  bool has_nan = false, any_ge = false;
-  for (int k = lane; k < nt; k += 32) {
-    double v = x_literal(s_den[k], f_hz);
-    if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
-    crit[k] = v;
-    has_nan |= isnan(v);
-    any_ge |= (v >= 1.0);
-    if (v > 1.0) first_gt = min(first_gt, k);
-  }
-  const int jstar = warp_min_i(first_gt);
-  const bool dead = __any_sync(0xffffffffu, has_nan) || !__any_sync(0xffffffffu, any_ge);
-  __syncwarp();
-  if (dead) {                                             // valid == False (lib:399) -> NaN (lib:407)
-    if (lane == 0) {
-      double res = CUDART_NAN;
-      if (nt == 1) {
-        // numpy's single-node np.interp has no NaN test: interp(NaN, [x0], [f0]) == f0.  A dead row of a
-        // one-node profile therefore still sees finite den/bmag/bpsi, every dh is NaN except the final
-        // 1e-6 (lib:416), and the reference returns alt_min + mu'(node 0) * 1e-6.
-        const double X = x_literal(s_den[0], f_hz);
-        double mup;
-        if (iso) {
-          mup = iso_mup(X, nullptr);
-        } else if (mode == 0) {
-          mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), g_psi[0], nullptr);
-        } else {
-          mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), g_psi[0], nullptr);
+  for (int rr = 0; rr < p.rows_per_warp; ++rr) {
+    const int r = (g * p.rows_per_warp + rr) * kRowsPerCta + wid;
+    if (r >= p.n_freq) break;
+    const int64_t out_idx = prof * p.n_freq + r;
+    const int64_t lrow = lprof * p.n_freq + r;
+    if (status != 0) {
+      if (lane == 0) { p.vh[out_idx] = CUDART_NAN; p.row_span[lrow] = CUDART_NAN; }
+      continue;
+    }
+    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+
+    // Critical curve at the nodes (lib:380-399): v_k = X_k (O) or X_k + Y_k (X) in the reference's rounding
+    // order.  The reference needs: does any v_k reach 1 (validity), the first k with v_k > 1 (jstar), the
+    // running max just below it (M) and v_jstar.  Evaluating 7 correctly rounded operations per node and
+    // frequency costs more than the grid loop when n_points is small, so the nodes are first screened with
+    // a_k = den_k * (cp^2/f^2) + b_k * (g_p/f), whose distance from the literal value is bounded by
+    // 13 ulp * (|X_k| + |Y_k|); only nodes whose screen value is within kScreenTol of a decision are
+    // evaluated literally, so every decision and every value that enters h_c is the literal one.
+    const double kx = (kCp * kCp) / __dmul_rn(f_hz, f_hz);
+    const double ky = (mode == 1) ? kGp / f_hz : 0.0;
+    const bool screen = !any_general && isfinite(kx) && isfinite(ky) && kx > 0.0;
+    int jstar = 0x7fffffff;
+    bool any_eq1 = false, has_nan = false;
+    double v_jstar = 0.0, M = -CUDART_INF;
+    if (screen) {
+      for (int k = lane; k < nt; k += 32) crit[k] = fma(s_b[k], ky, s_den[k] * kx);
+      __syncwarp();
+      int start = 0;
+      for (;;) {
+        int cand = 0x7fffffff;
+        for (int k = lane; k < nt; k += 32) {
+          if (k < start) continue;
+          const double tol = kScreenTol * (fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
+          if (crit[k] >= 1.0 - tol) { cand = k; break; }
         }
-        const double term = mup * kBackoff;
-        if (term == term && term != 0.0) res = term + alt_min;
+        cand = warp_min_i(cand);
+        if (cand == 0x7fffffff) break;
+        double v = x_literal(s_den[cand], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[cand], f_hz));
+        if (v > 1.0) { jstar = cand; v_jstar = v; break; }
+        if (v == 1.0) any_eq1 = true;
+        start = cand + 1;
       }
-      p.vh[out_idx] = res;
-      p.row_span[lrow] = CUDART_NAN;
-    }
-    return;
-  }
-  // ---- reflection height: np.interp(1.0, running max, alt) (lib:403-404) ----
-  double hcrit;
-  if (jstar == 0 || nt == 1) {
-    hcrit = s_alt[0];                                     // 1.0 < fcrit[0]: np.interp clamps left
-  } else if (jstar == 0x7fffffff) {
-    hcrit = s_alt[nt - 1];                                // running max ends exactly at 1.0
-  } else {
-    double pm = -CUDART_INF;
-    for (int k = lane; k < jstar; k += 32) pm = fmax(pm, crit[k]);
-    const double M = warp_max(pm);                        // cummax[jstar-1]
-    const int j = jstar - 1;
-    if (M == 1.0) {
-      hcrit = s_alt[j];
+      if (jstar != 0x7fffffff && jstar > 0) {
+        double amax = -CUDART_INF, smax = 0.0;
+        for (int k = lane; k < jstar; k += 32) {
+          amax = fmax(amax, crit[k]);
+          smax = fmax(smax, fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
+        }
+        amax = warp_max(amax);
+        const double thr = amax - 2.0 * kScreenTol * warp_max(smax);
+        for (int k = lane; k < jstar; k += 32) {
+          if (crit[k] >= thr) {
+            double v = x_literal(s_den[k], f_hz);
+            if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+            M = fmax(M, v);
+          }
+        }
+        M = warp_max(M);                                   // cummax[jstar-1], literal
+      }
     } else {
-      const double slope = __ddiv_rn(__dsub_rn(s_alt[j + 1], s_alt[j]), __dsub_rn(crit[jstar], M));
-      hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
+      int first_gt = 0x7fffffff;
+      bool any_ge = false;
+      for (int k = lane; k < nt; k += 32) {
+        double v = x_literal(s_den[k], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+        crit[k] = v;
+        has_nan |= isnan(v);
+        any_ge |= (v >= 1.0);
+        if (v > 1.0) first_gt = min(first_gt, k);
+      }
+      jstar = warp_min_i(first_gt);
+      has_nan = __any_sync(0xffffffffu, has_nan);
+      any_eq1 = __any_sync(0xffffffffu, any_ge);           // with jstar == none this means max == 1.0
+      __syncwarp();
+      if (jstar != 0x7fffffff && jstar > 0) {
+        double pm = -CUDART_INF;
+        for (int k = lane; k < jstar; k += 32) pm = fmax(pm, crit[k]);
+        M = warp_max(pm);
+        v_jstar = crit[jstar];
+      }
     }
-  }
-  if (lane == 0) {
-    const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
-    p.row_span[lrow] = __dsub_rn(hc, s_alt[0]);           // lib:413 (h_c - aalt[0])
+    const bool dead = has_nan || (jstar == 0x7fffffff && !any_eq1);
+    if (dead) {                                             // valid == False (lib:399) -> NaN (lib:407)
+      if (lane == 0) {
+        double res = CUDART_NAN;
+        if (nt == 1) {
+          // numpy's single-node np.interp has no NaN test: interp(NaN, [x0], [f0]) == f0.  A dead row of a
+          // one-node profile therefore still sees finite den/bmag/bpsi, every dh is NaN except the final
+          // 1e-6 (lib:416), and the reference returns alt_min + mu'(node 0) * 1e-6.
+          const double X = x_literal(s_den[0], f_hz);
+          double mup;
+          if (iso) {
+            mup = iso_mup(X, nullptr);
+          } else if (mode == 0) {
+            mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
+          } else {
+            mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
+          }
+          const double term = mup * kBackoff;
+          if (term == term && term != 0.0) res = term + alt_min;
+        }
+        p.vh[out_idx] = res;
+        p.row_span[lrow] = CUDART_NAN;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- reflection height: np.interp(1.0, running max, alt) (lib:403-404) ----
+    double hcrit;
+    if (jstar == 0 || nt == 1) {
+      hcrit = s_alt[0];                                     // 1.0 < fcrit[0]: np.interp clamps left
+    } else if (jstar == 0x7fffffff) {
+      hcrit = s_alt[nt - 1];                                // running max ends exactly at 1.0
+    } else {
+      const int j = jstar - 1;
+      if (M == 1.0) {
+        hcrit = s_alt[j];
+      } else {
+        const double slope = __ddiv_rn(__dsub_rn(s_alt[j + 1], s_alt[j]), __dsub_rn(v_jstar, M));
+        hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
+      }
+    }
+    if (lane == 0) {
+      const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
+      p.row_span[lrow] = __dsub_rn(hc, s_alt[0]);           // lib:413 (h_c - aalt[0])
+    }
+    __syncwarp();
   }
 }
 
@@ -468,13 +561,25 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   const int64_t tile = blockIdx.x;
   const int seg = (int)(tile % p.n_seg);
   const int64_t lrow = tile / p.n_seg;                    // row index inside this launch
-  const double span = p.row_span[lrow];
-  if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
-
+#ifdef PRHF_TRACE
+  if (p.trace && tid == 0) {
+    p.trace[(size_t)blockIdx.x * 8 + 0] = trace_smid();
+    p.trace[(size_t)blockIdx.x * 8 + 1] = trace_globaltimer();
+  }
+#endif
+  PRHF_TRACE_MARK(2);
   const int r = (int)(lrow % p.n_freq);
   const int64_t lprof = lrow / p.n_freq;
   const int64_t prof = p.profile_offset + lprof;
+  const int i0 = seg * p.seg_len;
+  const int i1 = min(p.n_points, i0 + p.seg_len);
+  // every load of the prologue is independent of the others: issue them together
+  const double span = p.row_span[lrow];
   const ProfileRecord rec = p.prof_rec[lprof];
+  const double f_mhz = p.freq[prof * p.freq_stride + r];
+  const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
+  if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
+  PRHF_TRACE_MARK(3);
   const int nt = rec.nt;
 
   int path;
@@ -493,8 +598,8 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   const double* g_alt = p.alt + prof * p.alt_stride;
 
   RowConst rc;
-  rc.f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);
-  rc.alt0 = g_alt[0];
+  rc.f_hz = __dmul_rn(f_mhz, 1e6);
+  rc.alt0 = rec.alt0;
   rc.span = span;
   rc.inv_dalt = rec.inv_dalt;
   rc.nt = nt;
@@ -502,49 +607,72 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   const double ky = kGp / rc.f_hz;
   const bool const_mup = !(span > 0.0) || nt == 1;         // h_c <= alt0: every point clamps to level 0
 
-  // ---- node window of this tile ----
-  const int i0 = seg * p.seg_len;
-  const int i1 = min(p.n_points, i0 + p.seg_len);
-  if (tid == 0 || tid == 32) {
-    int j = 0;
-    if (!const_mup) {
-      const int i = (tid == 0) ? i0 : (i1 - 1);
-      const double h = __dadd_rn(__dmul_rn(__ldg(p.mult + i), span), rc.alt0);
-      // guess from the mean spacing, verify against the global altitude table, bisect if needed
-      const int gj = min(max(__double2int_rd((h - rc.alt0) * rec.inv_dalt), 0), nt - 1);
-      if (h >= g_alt[gj] && (gj == nt - 1 || h < g_alt[gj + 1])) j = gj;
-      else j = max(bracket_in<1>(h, g_alt, 0, nt - 1), 0);
+  // ---- node window of this tile: brackets of its first and last grid point ----
+  if (const_mup) {
+    rc.jlo = rc.jhi = 0;
+  } else {
+    const double h_lo = __dadd_rn(__dmul_rn(m_lo, span), rc.alt0);
+    const double h_hi = __dadd_rn(__dmul_rn(m_hi, span), rc.alt0);
+    const int g_lo = min(max(__double2int_rd((h_lo - rc.alt0) * rec.inv_dalt), 0), nt - 1);
+    const int g_hi = min(max(__double2int_rd((h_hi - rc.alt0) * rec.inv_dalt), 0), nt - 1);
+    if (rec.flags & kFlagUniformAlt) {
+      // levels sit within a quarter step of the uniform grid: the guess is the bracket to +-1
+      rc.jlo = max(g_lo - 1, 0);
+      rc.jhi = min(g_hi + 1, nt - 1);
+    } else {
+      if (tid == 0 || tid == 32) {
+        const double h = (tid == 0) ? h_lo : h_hi;
+        const int gj = (tid == 0) ? g_lo : g_hi;
+        int j;
+        if (h >= g_alt[gj] && (gj == nt - 1 || h < g_alt[gj + 1])) j = gj;
+        else j = max(bracket_in<1>(h, g_alt, 0, nt - 1), 0);
+        sc.bcast_i[tid >> 5] = j;
+      }
+      __syncthreads();
+      rc.jlo = min(sc.bcast_i[0], sc.bcast_i[1]);
+      rc.jhi = max(sc.bcast_i[0], sc.bcast_i[1]);
     }
-    sc.bcast_i[tid >> 5] = j;
   }
-  __syncthreads();
-  rc.jlo = min(sc.bcast_i[0], sc.bcast_i[1]);
-  rc.jhi = max(sc.bcast_i[0], sc.bcast_i[1]);
+  PRHF_TRACE_MARK(4);
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
   for (int q = tid; q < n_stage; q += kThreads) {
     const int k = rc.jlo + q;
+    const bool inner = k + 1 < nt;
     const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
-    double sd = 0.0, sb = 0.0, sp = 0.0;
-    if (k + 1 < nt) {                                     // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
-      const double dx = __dsub_rn(g_alt[k + 1], a0);
-      sd = __ddiv_rn(__dsub_rn(g_den[k + 1], d0), dx);
-      sb = __ddiv_rn(__dsub_rn(g_b[k + 1], b0), dx);
-      sp = __ddiv_rn(__dsub_rn(g_psi[k + 1], p0), dx);
-    }
+    const double a1 = inner ? g_alt[k + 1] : a0, d1 = inner ? g_den[k + 1] : d0;
+    const double b1 = inner ? g_b[k + 1] : b0, p1 = inner ? g_psi[k + 1] : p0;
     Node nd;
     nd.alt = a0;
     if (fast) {
-      double sn, cs;
-      sincos(p0 * kDeg2Rad, &sn, &cs);
-      nd.x = d0 * kx; nd.sx = sd * kx; nd.y = b0 * ky; nd.sy = sb * ky; nd.srad = sp * kDeg2Rad; nd.sn = sn; nd.cs = cs;
+      // slopes through one fast reciprocal (<= 2 ulp from numpy's quotient; the literal paths divide)
+      const double inv_dx = inner ? rcp_fast(a1 - a0) : 0.0;
+      nd.x = d0 * kx;
+      nd.sx = ((d1 - d0) * kx) * inv_dx;
+      nd.y = b0 * ky;
+      nd.sy = ((b1 - b0) * ky) * inv_dx;
+      nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
+      if (path == kPathFast0) {
+        nd.sn = rec.sn0;
+        nd.cs = rec.cs0;
+      } else {
+        sincos(p0 * kDeg2Rad, &nd.sn, &nd.cs);
+      }
     } else {
+      double sd = 0.0, sb = 0.0, sp = 0.0;
+      if (inner) {                                        // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
+        const double dx = __dsub_rn(a1, a0);
+        sd = __ddiv_rn(__dsub_rn(d1, d0), dx);
+        sb = __ddiv_rn(__dsub_rn(b1, b0), dx);
+        sp = __ddiv_rn(__dsub_rn(p1, p0), dx);
+      }
       nd.x = d0; nd.sx = sd; nd.y = b0; nd.sy = sb; nd.srad = sp; nd.sn = p0; nd.cs = 0.0;
     }
     nodes[q] = nd;
   }
   __syncthreads();
+  PRHF_TRACE_MARK(5);
 
   // ---- grid points of the tile ----
   double acc;
@@ -582,7 +710,9 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   }
 
   // ---- reduce, finish (lib:288-292) ----
+  PRHF_TRACE_MARK(6);
   const double s_tile = block_sum(acc, sc);
+  PRHF_TRACE_MARK(7);
   if (tid != 0) return;
   double total = s_tile;
   if (p.n_seg > 1) {
@@ -674,7 +804,7 @@ __global__ void math_selftest_kernel(int n, double* __restrict__ err) {
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-size_t vfo_rows_smem_bytes(int n_alt) { return sizeof(double) * (3 + kRowsPerCta) * (size_t)n_alt; }
+size_t vfo_rows_smem_bytes(int n_alt) { return sizeof(double) * (4 + kRowsPerCta) * (size_t)n_alt; }
 size_t vfo_tile_smem_bytes(int n_alt) { return sizeof(Node) * (size_t)n_alt; }
 size_t vfo_smem_bytes(int n_alt) {
   const size_t a = vfo_rows_smem_bytes(n_alt), b = vfo_tile_smem_bytes(n_alt);
@@ -685,7 +815,8 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
   const size_t smem = vfo_rows_smem_bytes(p.n_alt);
   cudaError_t e = cudaFuncSetAttribute(vfo_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int chunks = (p.n_freq + kRowsPerCta - 1) / kRowsPerCta;
+  const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
+  const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   vfo_rows_kernel<<<(unsigned)(n_profiles * chunks), kThreads, smem, stream>>>(p, mode);
   return cudaGetLastError();
 }

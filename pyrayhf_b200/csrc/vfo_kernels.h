@@ -15,13 +15,16 @@ constexpr int kFlagGeneral = 2;   // non-finite node values / non-increasing alt
 constexpr int kFlagFailed = 4;    // status != 0
 constexpr int kFlagPsiConst = 8;  // field angle identical at every level below the peak
 constexpr int kFlagPsiSmall = 16; // per-level field-angle steps <= kSmallRotateStep
+constexpr int kFlagUniformAlt = 32; // levels within a quarter step of alt0 + k * mean step: the bracket guess is exact +-1
 
-struct ProfileRecord {            // 32 bytes per profile, written by K1, read by K2
+struct __align__(16) ProfileRecord {  // 64 bytes per profile, written by K1, read by K2
   int nt;                         // truncated length = argmax(den) (lib:371)
   int flags;
   double alt_min;                 // np.min(alt) (lib:507)
   double inv_dalt;                // (nt-1)/(alt[nt-1]-alt[0]); bracket guess for near-uniform grids
-  double pad;
+  double alt0;                    // alt[0]
+  double sn0, cs0;                // sin / cos of the field angle at level 0 (all levels when kFlagPsiConst)
+  double pad[2];
 };
 
 struct VfoParams {
@@ -39,12 +42,14 @@ struct VfoParams {
   int n_points;
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
+  int rows_per_warp;       // K1: sounding frequencies handled by one warp (CTA = 8 warps)
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null
   ProfileRecord* prof_rec; // [profiles_in_launch]
   double* row_span;        // [rows_in_launch]  h_c - alt0, NaN = row finished by K1
   double* partial;         // [rows_in_launch x n_seg] when n_seg > 1
   unsigned* counter;       // [rows_in_launch], zero on entry, zero on exit
+  long long* trace;        // developer phase trace [tiles x 8] (PRHF_TRACE builds), else null
 };
 
 size_t vfo_smem_bytes(int n_alt);

@@ -221,3 +221,35 @@ def test_fast_math_accuracy(vfo):
     e_rcp, e_rsqrt = errs[0], errs[1]
     assert 0.0 <= e_rcp < 4.5e-16, e_rcp
     assert 0.0 <= e_rsqrt < 4.5e-16, e_rsqrt
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_critical_frequency_ulp_sweep(vfo, golden, mode):
+    """Frequencies within a few ulp of making X (or X+Y) == 1 exactly at a profile level: the row-setup
+    kernel's screened scan must take every validity / bracket decision exactly as the literal one."""
+    fx = golden.fixtures
+    den, bmag, bpsi, alt = (fx["Day_" + k] for k in ("den", "bmag", "bpsi", "alt"))
+    nt = int(np.argmax(den))
+    freqs = []
+    for k in (5, 40, 120, nt - 2, nt - 1):
+        fp = np.sqrt(den[k]) * 8.97866275                 # plasma frequency at level k [Hz]
+        if mode == 'X':
+            fh = 2.799249247e10 * bmag[k]
+            f0 = 0.5 * (fh + np.sqrt(fh * fh + 4 * fp * fp))   # X + Y = 1
+        else:
+            f0 = fp
+        f0 /= 1e6
+        for j in range(-6, 7):
+            f = f0
+            for _ in range(abs(j)):
+                f = np.nextafter(f, np.inf if j > 0 else -np.inf)
+            freqs.append(f)
+    freqs = np.array(freqs)
+    got = vfo.vertical_forward_operator(freqs, den, bmag, bpsi, alt, mode, 300)
+    ref = vfo_oracle.vertical_forward_operator(freqs, den, bmag, bpsi, alt, mode, 300)
+    tru = scalar.vertical_forward_operator(freqs, den, bmag, bpsi, alt, mode, 300, variant=1,
+                                           multiplier=vfo_oracle.stretch_multiplier(300))
+    assert np.isnan(ref).any() and np.isfinite(ref).any()
+    # rows whose reflection level is a flat spot of the profile are ill-conditioned in h_c itself;
+    # the mask must still agree exactly and the values to 1e-9 (X) / rounding ball (O)
+    assert_parity(got, ref, tru, mode, "ulp sweep")

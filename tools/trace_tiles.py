@@ -1,0 +1,64 @@
+"""Developer tool: per-CTA phase timeline of the tile kernel for the bench workload (needs `make trace`)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pyrayhf_b200 import _cabi, synth  # noqa: E402
+
+_cabi.LIB_PATH = os.path.join(ROOT, "pyrayhf_b200", "csrc", "libpyrayhf_b200_trace.so")
+import pyrayhf_b200  # noqa: E402
+
+vp = ctypes.c_void_p
+
+
+def main():
+    dev = torch.device("cuda:0")
+    den, bmag, bpsi, alt = synth.bench_day_profile()
+    freq = synth.default_freq()
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den[None], bmag[None], bpsi[None], alt)]
+    ctx = _cabi.context(0)
+    L = ctx.lib
+    n_tiles = 174 * 32
+    L.prhf_debug_trace_alloc.argtypes = [vp, ctypes.c_int64]
+    L.prhf_debug_trace_read.argtypes = [vp, ctypes.c_int64, vp]
+    for _ in range(3):
+        pyrayhf_b200.vertical_forward_operator_batched(*t, 'X', 20000)
+    torch.cuda.synchronize()
+    L.prhf_debug_trace_alloc(ctx.handle, n_tiles)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()
+    pyrayhf_b200.vertical_forward_operator_batched(*t, 'X', 20000)
+    out = np.zeros((n_tiles, 8), dtype=np.int64)
+    L.prhf_debug_trace_read(ctx.handle, n_tiles, vp(out.ctypes.data))
+    used = out[:, 1] != 0
+    tr = out[used]
+    live = tr[:, 7] != 0
+    print("tiles launched", used.sum(), "live", live.sum())
+    g0 = tr[:, 1].min()
+    print("globaltimer span of CTA starts: %.1f us" % ((tr[:, 1].max() - g0) / 1e3))
+    lt = tr[live]
+    names = ["span-load", "window", "staging", "loop", "reduce"]
+    for k, nm in enumerate(names):
+        d = lt[:, 3 + k] - lt[:, 2 + k]
+        print("%-10s cycles: median %7.0f  p10 %7.0f  p90 %7.0f  max %7.0f" % (nm, np.median(d), np.percentile(d, 10),
+                                                                          np.percentile(d, 90), d.max()))
+    tot = lt[:, 7] - lt[:, 2]
+    print("tile total cycles: median %.0f p90 %.0f max %.0f" % (np.median(tot), np.percentile(tot, 90), tot.max()))
+    dead = tr[~live]
+    # start-time histogram in 2 us bins
+    st = (tr[:, 1] - g0) / 1e3
+    hist, edges = np.histogram(st, bins=np.arange(0, st.max() + 2, 2.0))
+    print("CTA starts per 2us bin:", hist.tolist())
+    # per-SM busy: number of tiles per SM
+    sm = lt[:, 0]
+    cnt = np.bincount(sm, minlength=148)
+    print("live tiles per SM: min %d max %d" % (cnt.min(), cnt.max()))
+
+
+if __name__ == "__main__":
+    main()
