@@ -71,3 +71,16 @@ def test_errors_match(ref):
         neg[0] = -5.0
         with pytest.raises(ValueError):
             impl(f, neg, bmag, bpsi, alt, 'X', 10)
+
+
+def test_install_rebinds_reference_global(ref):
+    """pyrayhf_b200.install() swaps the module global that model_VH resolves at call time (lib:589)."""
+    import pyrayhf_b200
+    original = ref.vertical_forward_operator
+    try:
+        pyrayhf_b200.install()
+        assert ref.vertical_forward_operator is pyrayhf_b200.vertical_forward_operator
+        assert ref.model_VH.__globals__["vertical_forward_operator"] is pyrayhf_b200.vertical_forward_operator
+    finally:
+        pyrayhf_b200.uninstall()
+    assert ref.vertical_forward_operator is original
