@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpyrayhf_b200.so")
+LIB_PATH = os.environ.get("PRHF_LIB_PATH") or os.path.join(_HERE, "csrc", "libpyrayhf_b200.so")   # env: developer variants
 
 OK = 0
 ERR_INVALID_ARG = 1

@@ -7,6 +7,7 @@
 // pinned-memory staging of the host-buffer entry point.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -42,6 +43,14 @@ struct prhf_ctx {
   int seg_len_override = 0;          // PRHF_SEG_LEN (tuning / tests)
   int64_t target_tiles = 0;          // PRHF_TARGET_TILES
   long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
+  size_t trace_k1_off = 0;           // K1 entries start here (in long longs)
+  // planned mode (small batches): tile plan, compact tile list, K1 completion counter
+  unsigned* live_count = nullptr;    // [2], one per call parity
+  prhf::LiveRow* live_list = nullptr;
+  size_t live_list_cap = 0;
+  int plan_parity = 0;
+  int max_smem_per_sm = 0;
+  int planned_max_rows = 4096;       // PRHF_PLANNED_MAX_ROWS
 };
 
 namespace {
@@ -109,6 +118,21 @@ int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
   return PRHF_OK;
 }
 
+int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
+  if (!ctx->live_count) {
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_count, 2 * sizeof(unsigned)));
+    PRHF_CUDA(ctx, cudaMemset(ctx->live_count, 0, 2 * sizeof(unsigned)));
+  }
+  if (n_rows > ctx->live_list_cap) {
+    if (ctx->live_list) cudaFree(ctx->live_list);
+    ctx->live_list = nullptr;
+    ctx->live_list_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_list, sizeof(prhf::LiveRow) * n_rows));
+    ctx->live_list_cap = n_rows;
+  }
+  return PRHF_OK;
+}
+
 int ensure_workspace(prhf_ctx* ctx, size_t n_partial, size_t n_counter) {
   if (n_partial > ctx->partial_cap) {
     if (ctx->partial) cudaFree(ctx->partial);
@@ -146,7 +170,7 @@ void choose_tiling(const prhf_ctx* ctx, int64_t rows, int n_points, int* seg_len
   const int max_seg = std::max(1, n_points / 1024);
   want = std::max<int64_t>(1, std::min<int64_t>(want, max_seg));
   int sl = (int)((n_points + want - 1) / want);
-  sl = ((sl + prhf::kThreads - 1) / prhf::kThreads) * prhf::kThreads;
+  sl = ((sl + 2 * prhf::kTileThreads - 1) / (2 * prhf::kTileThreads)) * (2 * prhf::kTileThreads);
   sl = std::max(sl, 1);
   *seg_len = sl;
   *n_seg = (n_points + sl - 1) / sl;
@@ -205,6 +229,8 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+  if (const char* s = getenv("PRHF_PLANNED_MAX_ROWS")) ctx->planned_max_rows = atoi(s);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -223,6 +249,8 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   for (auto& kv : ctx->mult) cudaFree(kv.second);
   if (ctx->partial) cudaFree(ctx->partial);
   if (ctx->counter) cudaFree(ctx->counter);
+  if (ctx->live_count) cudaFree(ctx->live_count);
+  if (ctx->live_list) cudaFree(ctx->live_list);
   if (ctx->prof_rec) cudaFree(ctx->prof_rec);
   if (ctx->row_span) cudaFree(ctx->row_span);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
@@ -244,14 +272,15 @@ int prhf_debug_trace_alloc(prhf_ctx* ctx, int64_t n_tiles) {
   DeviceGuard g(ctx->device);
   if (ctx->trace) cudaFree(ctx->trace);
   ctx->trace = nullptr;
-  PRHF_CUDA(ctx, cudaMalloc(&ctx->trace, sizeof(long long) * 8 * (size_t)n_tiles));
-  PRHF_CUDA(ctx, cudaMemset(ctx->trace, 0, sizeof(long long) * 8 * (size_t)n_tiles));
+  PRHF_CUDA(ctx, cudaMalloc(&ctx->trace, sizeof(long long) * 8 * (size_t)(n_tiles + 4096)));
+  PRHF_CUDA(ctx, cudaMemset(ctx->trace, 0, sizeof(long long) * 8 * (size_t)(n_tiles + 4096)));
+  ctx->trace_k1_off = 8 * (size_t)n_tiles;
   return PRHF_OK;
 }
 int prhf_debug_trace_read(prhf_ctx* ctx, int64_t n_tiles, long long* out) {
   DeviceGuard g(ctx->device);
   PRHF_CUDA(ctx, cudaDeviceSynchronize());
-  PRHF_CUDA(ctx, cudaMemcpy(out, ctx->trace, sizeof(long long) * 8 * (size_t)n_tiles, cudaMemcpyDeviceToHost));
+  PRHF_CUDA(ctx, cudaMemcpy(out, ctx->trace, sizeof(long long) * 8 * (size_t)(n_tiles + 4096), cudaMemcpyDeviceToHost));
   return PRHF_OK;
 }
 #endif
@@ -278,8 +307,32 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
   if (rc != PRHF_OK) return rc;
 
   const int64_t rows_total = n_profiles * (int64_t)n_freq;
+  const bool literal = (flags & PRHF_FLAG_LITERAL) != 0;
+  const int ctas_per_sm = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm);
+  const int slots = ctx->sm_count * ctas_per_sm;
+
+  // Small batches (fewer rows than a few waves of tiles): planned mode.  K1's last CTA counts the rows
+  // that reflect and sizes the segments so that the live tiles fill the resident-CTA slots; K2 strides
+  // over the compact tile list.  Large batches: direct mode, one tile per row.
+  const bool planned = ctx->seg_len_override <= 0 && rows_total <= (int64_t)ctx->planned_max_rows &&
+                       n_points >= 2048;
   int seg_len = 0, n_seg = 0;
-  choose_tiling(ctx, rows_total, n_points, &seg_len, &n_seg);
+  int n_cand = 0, cand_seg[prhf::kMaxPlanCand] = {0}, cand_len[prhf::kMaxPlanCand] = {0};
+  if (planned) {
+    n_seg = std::max(1, std::min(prhf::kMaxPlanCand, n_points / 1024));   // upper bound (stride of the partials)
+    seg_len = n_points;                                       // unused by the kernels in planned mode
+    // candidate tilings: ns segments of a length that is a multiple of two points per thread
+    const int quantum = 2 * prhf::kTileThreads;
+    for (int ns = 1; ns <= n_seg && n_cand < prhf::kMaxPlanCand; ++ns) {
+      const int sl = ((n_points + ns - 1) / ns + quantum - 1) / quantum * quantum;
+      if ((n_points + sl - 1) / sl != ns) continue;           // rounding made a segment empty
+      cand_seg[n_cand] = ns;
+      cand_len[n_cand] = sl;
+      ++n_cand;
+    }
+  } else {
+    choose_tiling(ctx, rows_total, n_points, &seg_len, &n_seg);
+  }
 
   // A launch covers at most max_tiles tiles (grid.x limit) and max_rows rows (hand-off workspace);
   // profiles are chunked accordingly.
@@ -294,6 +347,10 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
   if (rc != PRHF_OK) return rc;
   if (n_seg > 1) {
     rc = ensure_workspace(ctx, (size_t)rows_launch * n_seg, (size_t)rows_launch);
+    if (rc != PRHF_OK) return rc;
+  }
+  if (planned) {
+    rc = ensure_plan(ctx, (size_t)rows_launch);
     if (rc != PRHF_OK) return rc;
   }
   // K1 granularity: 8 rows per CTA while the launch is small (latency matters), whole profiles per CTA
@@ -329,8 +386,25 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.partial = ctx->partial;
     P.counter = ctx->counter;
     P.trace = ctx->trace;
+    if (planned) {
+      P.live_count = ctx->live_count + ctx->plan_parity;
+      P.live_count_other = ctx->live_count + (1 - ctx->plan_parity);
+      P.live_list = ctx->live_list;
+      ctx->plan_parity ^= 1;
+    } else {
+      P.live_count = P.live_count_other = nullptr;
+      P.live_list = nullptr;
+    }
+    P.rows_in_launch = np * n_freq;
+    P.max_seg = n_seg;
+    P.slots = slots;
+    P.n_cand = n_cand;
+    for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
+    P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
     PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
-    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, (flags & PRHF_FLAG_LITERAL) != 0, np * tiles_per_profile, stream));
+    // planned mode: enough CTAs for two waves of slots; they stride over however many tiles K1 planned
+    const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots) : np * tiles_per_profile;
+    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
     ctx->launches += 2;
   }
   return PRHF_OK;

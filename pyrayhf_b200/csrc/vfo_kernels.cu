@@ -42,8 +42,13 @@ __device__ __forceinline__ int trace_smid() {
   asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
   return s;
 }
+#define PRHF_TRACE_K1(slot)                                                                      \
+  do {                                                                                           \
+    if (p.trace_k1 && threadIdx.x == 0) p.trace_k1[(size_t)blockIdx.x * 8 + (slot)] = clock64(); \
+  } while (0)
 #else
 #define PRHF_TRACE_MARK(slot) do { } while (0)
+#define PRHF_TRACE_K1(slot) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -64,11 +69,11 @@ __global__ void grid_multiplier_kernel(int n, int n_padded, double step, double*
 }
 
 // ------------------------------------------------------------------------------------------
-// warp / block helpers (kThreads = 256 = 8 warps)
+// warp / block helpers (any block size that is a multiple of 32, at most kMaxWarps warps)
 // ------------------------------------------------------------------------------------------
 struct BlockScratch {
-  double d[kThreads / 32];
-  int i[kThreads / 32];
+  double d[kMaxWarps];
+  int i[kMaxWarps];
   int bcast_i[4];
 };
 
@@ -103,7 +108,7 @@ __device__ __forceinline__ double block_sum(double v, BlockScratch& sc) {
   double r = 0.0;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) r += sc.d[k];
+    for (int k = 0; k < kMaxWarps; ++k) r += (k < (int)(blockDim.x >> 5)) ? sc.d[k] : 0.0;
   }
   return r;
 }
@@ -116,7 +121,7 @@ __device__ __forceinline__ double block_max(double v, BlockScratch& sc) {
   __syncthreads();
   double r = sc.d[0];
 #pragma unroll
-  for (int k = 1; k < kThreads / 32; ++k) r = fmax(r, sc.d[k]);
+  for (int k = 1; k < kMaxWarps; ++k) if (k < (int)(blockDim.x >> 5)) r = fmax(r, sc.d[k]);
   return r;
 }
 __device__ __forceinline__ double block_min(double v, BlockScratch& sc) {
@@ -127,7 +132,7 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& sc) {
   __syncthreads();
   double r = sc.d[0];
 #pragma unroll
-  for (int k = 1; k < kThreads / 32; ++k) r = fmin(r, sc.d[k]);
+  for (int k = 1; k < kMaxWarps; ++k) if (k < (int)(blockDim.x >> 5)) r = fmin(r, sc.d[k]);
   return r;
 }
 
@@ -153,9 +158,64 @@ __device__ __forceinline__ int block_argmax(double v, int idx, BlockScratch& sc)
   double bv = sc.d[0];
   int bi = sc.i[0];
 #pragma unroll
-  for (int k = 1; k < kThreads / 32; ++k)
-    if (arg_precedes(sc.d[k], sc.i[k], bv, bi)) { bv = sc.d[k]; bi = sc.i[k]; }
+  for (int k = 1; k < kMaxWarps; ++k)
+    if (k < (int)(blockDim.x >> 5) && arg_precedes(sc.d[k], sc.i[k], bv, bi)) { bv = sc.d[k]; bi = sc.i[k]; }
   return bi;
+}
+
+// ---- K1 profile reductions: one shared-memory round each ----
+// Total order key for np.argmax: NaN above everything, then the value; ties broken by the lower index.
+__device__ __forceinline__ long long argmax_key(double v) {
+  long long b = __double_as_longlong(v);
+  b = (b < 0) ? (b ^ 0x7fffffffffffffffLL) : b;           // sign-magnitude -> two's-complement order
+  return isnan(v) ? 0x7fffffffffffffffLL : b;
+}
+struct ProfileReduce1 { int nt; double alt_min; };
+__device__ __forceinline__ ProfileReduce1 block_argmax_min(double v, int idx, double amin, long long* s_key,
+                                                           int* s_idx, double* s_min) {
+  long long key = argmax_key(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    const double om = __shfl_xor_sync(0xffffffffu, amin, o);
+    if (ok > key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+    amin = fmin(amin, om);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_key[wid] = key; s_idx[wid] = idx; s_min[wid] = amin; }
+  __syncthreads();
+  ProfileReduce1 r;
+  long long bk = s_key[0];
+  r.nt = s_idx[0];
+  r.alt_min = s_min[0];
+#pragma unroll
+  for (int k = 1; k < kThreads / 32; ++k) {
+    if (s_key[k] > bk || (s_key[k] == bk && s_idx[k] < r.nt)) { bk = s_key[k]; r.nt = s_idx[k]; }
+    r.alt_min = fmin(r.alt_min, s_min[k]);
+  }
+  return r;
+}
+struct ProfileReduce2 { double bmax, step_max; int flags; };
+__device__ __forceinline__ ProfileReduce2 block_max2_or(double a, double b, int flags, double* s_a, double* s_b,
+                                                        int* s_f) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_a[wid] = a; s_b[wid] = b; s_f[wid] = flags; }
+  __syncthreads();
+  ProfileReduce2 r{s_a[0], s_b[0], s_f[0]};
+#pragma unroll
+  for (int k = 1; k < kThreads / 32; ++k) {
+    r.bmax = fmax(r.bmax, s_a[k]);
+    r.step_max = fmax(r.step_max, s_b[k]);
+    r.flags |= s_f[k];
+  }
+  return r;
 }
 
 // numpy binary_search_with_guess outcome restricted to [lo, hi]: last j in [lo, hi] with xp[j] <= x,
@@ -195,6 +255,7 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
   const double* g_psi = p.bpsi + prof * A;
   const double* g_alt = p.alt + prof * p.alt_stride;
 
+  PRHF_TRACE_K1(0);
   // ---- stage the whole profile with all loads in flight at once (one DRAM latency), then
   //      argmax(den) (lib:371) and min(alt) (lib:507) ----
   double best_v = -CUDART_INF;
@@ -212,11 +273,18 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     if (arg_precedes(d, k, best_v, best_i)) { best_v = d; best_i = k; }
     amin = fmin(amin, a);
   }
-  const int nt = block_argmax(best_v, best_i, sc);      // truncated length = index of the peak (syncs)
-  const double alt_min = block_min(amin, sc);
+  PRHF_TRACE_K1(1);
+  __shared__ long long s_key[kThreads / 32];
+  __shared__ int s_ri[kThreads / 32];
+  __shared__ double s_ra[kThreads / 32], s_rb[kThreads / 32];
+  __syncthreads();                                      // the staged profile is visible to every warp
+  const ProfileReduce1 r1 = block_argmax_min(best_v, best_i, amin, s_key, s_ri, s_ra);
+  const int nt = r1.nt;                                 // truncated length = index of the peak
+  const double alt_min = r1.alt_min;
+  PRHF_TRACE_K1(2);
 
   // ---- node checks over [0, nt): negative density, non-finite values, angle steps, grid uniformity, max|B| ----
-  bool neg = false, general = false, nonuniform = false;
+  int chk = 0;                                          // bit 0 negative density, 1 general path, 2 non-uniform grid
   double bmax = 0.0, step_max = 0.0;
   const double alt0 = s_alt[0];
   const double mean_step = (nt > 1) ? (s_alt[nt - 1] - alt0) / (double)(nt - 1) : 1.0;
@@ -224,28 +292,32 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     const double d = s_den[k];
     const double b = s_b[k];
     const double ps = s_psi[k];
-    neg |= (d < 0.0);
-    general |= !(isfinite(d) && isfinite(b) && isfinite(ps) && isfinite(s_alt[k]));
+    const double a = s_alt[k];
+    if (d < 0.0) chk |= 1;
+    // finite <=> (x - x) == 0
+    if (!(((d - d) + (b - b)) + ((ps - ps) + (a - a)) == 0.0)) chk |= 2;
     bmax = fmax(bmax, fabs(b));
-    nonuniform |= !(fabs(s_alt[k] - fma((double)k, mean_step, alt0)) <= 0.25 * mean_step);
+    if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 0.25 * mean_step)) chk |= 4;
     if (k + 1 < nt) {
-      general |= !(__dsub_rn(s_alt[k + 1], s_alt[k]) > 0.0);
+      if (!(__dsub_rn(s_alt[k + 1], a) > 0.0)) chk |= 2;
       const double step = fabs(__dsub_rn(s_psi[k + 1], ps)) * kDeg2Rad;
-      general |= !(step <= kMaxRotateStep);
+      if (!(step <= kMaxRotateStep)) chk |= 2;
       step_max = fmax(step_max, step);
     }
   }
-  const bool any_neg = __syncthreads_or(neg);
-  const bool any_general = __syncthreads_or(general);
-  const bool any_nonuniform = __syncthreads_or(nonuniform);
+  __syncthreads();                                      // s_key/s_ri/s_ra are free again
+  const ProfileReduce2 r2 = block_max2_or(bmax, step_max, chk, s_ra, s_rb, s_ri);
+  bmax = r2.bmax;
+  step_max = r2.step_max;
+  const bool any_neg = (r2.flags & 1) != 0;
+  const bool any_general = (r2.flags & 2) != 0;
+  const bool any_nonuniform = (r2.flags & 4) != 0;
   const int status = (nt == 0) ? 2 : (any_neg ? 1 : 0);  // lib:399 IndexError / lib:93-94 ValueError
 
   // Unmagnetised switch (lib:201), decided per profile from the node values: isotropic iff
   // g_p * max|B| / min|f| < 1e-12 over the profile's frequencies.  (The reference takes nanmax|Y|
   // over the regridded [F x N] array of one call; the two differ only for |B| ~ 1e-17 T.)
   bool iso = false;
-  bmax = block_max(bmax, sc);
-  step_max = block_max(step_max, sc);
   if (status == 0 && bmax < 1e-9) {
     double fmin_abs = CUDART_INF;
     for (int k = tid; k < p.n_freq; k += kThreads) {
@@ -270,6 +342,7 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     p.prof_rec[lprof] = rec;
     if (p.status) p.status[prof] = status;
   }
+  PRHF_TRACE_K1(3);
   // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
   double* crit = s_crit + (size_t)wid * A;
   for (int rr = 0; rr < p.rows_per_warp; ++rr) {
@@ -397,10 +470,19 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     }
     if (lane == 0) {
       const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
-      p.row_span[lrow] = __dsub_rn(hc, s_alt[0]);           // lib:413 (h_c - aalt[0])
+      const double span = __dsub_rn(hc, s_alt[0]);          // lib:413 (h_c - aalt[0])
+      p.row_span[lrow] = span;
+      if (p.live_count) {                                   // planned mode: compact list of rows that reflect
+        LiveRow e;
+        e.row = (int)lrow;
+        e.pad = 0;
+        e.span = span;
+        p.live_list[atomicAdd(p.live_count, 1u)] = e;
+      }
     }
     __syncwarp();
   }
+  PRHF_TRACE_K1(4);
 }
 
 // ==========================================================================================
@@ -527,7 +609,7 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
                                            int i0, int i1, int n_points, double mup0) {
   double acc0 = 0.0, acc1 = 0.0;
   const double2* m2 = reinterpret_cast<const double2*>(m);
-  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kThreads) {
+  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kTileThreads) {
     const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
     const double mn = __ldg(m + i + 2);
     const double h0 = __dadd_rn(__dmul_rn(mm.x, rc.span), rc.alt0);  // lib:413
@@ -553,14 +635,12 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
   return acc0 + acc1;
 }
 
+// One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ BlockScratch sc;
+__device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span, const int seg,
+                                          const int n_seg, const int seg_len, unsigned char* smem_raw,
+                                          BlockScratch& sc) {
   const int tid = threadIdx.x;
-  const int64_t tile = blockIdx.x;
-  const int seg = (int)(tile % p.n_seg);
-  const int64_t lrow = tile / p.n_seg;                    // row index inside this launch
 #ifdef PRHF_TRACE
   if (p.trace && tid == 0) {
     p.trace[(size_t)blockIdx.x * 8 + 0] = trace_smid();
@@ -571,10 +651,9 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   const int r = (int)(lrow % p.n_freq);
   const int64_t lprof = lrow / p.n_freq;
   const int64_t prof = p.profile_offset + lprof;
-  const int i0 = seg * p.seg_len;
-  const int i1 = min(p.n_points, i0 + p.seg_len);
+  const int i0 = seg * seg_len;
+  const int i1 = min(p.n_points, i0 + seg_len);
   // every load of the prologue is independent of the others: issue them together
-  const double span = p.row_span[lrow];
   const ProfileRecord rec = p.prof_rec[lprof];
   const double f_mhz = p.freq[prof * p.freq_stride + r];
   const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
@@ -620,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
       rc.jlo = max(g_lo - 1, 0);
       rc.jhi = min(g_hi + 1, nt - 1);
     } else {
-      if (tid == 0 || tid == 32) {
+      if (tid == 0 || tid == 32) {                        // kTileThreads >= 64
         const double h = (tid == 0) ? h_lo : h_hi;
         const int gj = (tid == 0) ? g_lo : g_hi;
         int j;
@@ -637,7 +716,7 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
-  for (int q = tid; q < n_stage; q += kThreads) {
+  for (int q = tid; q < n_stage; q += kTileThreads) {
     const int k = rc.jlo + q;
     const bool inner = k + 1 < nt;
     const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
@@ -715,19 +794,57 @@ __global__ void __launch_bounds__(kThreads, 3) vfo_tile_kernel(const VfoParams p
   PRHF_TRACE_MARK(7);
   if (tid != 0) return;
   double total = s_tile;
-  if (p.n_seg > 1) {
-    double* part = p.partial + lrow * p.n_seg;
+  if (n_seg > 1) {
+    double* part = p.partial + lrow * p.max_seg;
     __stcg(part + seg, s_tile);
     __threadfence();
     const unsigned prev = atomicAdd(p.counter + lrow, 1u);
-    if (prev != (unsigned)(p.n_seg - 1)) return;
+    if (prev != (unsigned)(n_seg - 1)) return;
     __threadfence();
     total = 0.0;
-    for (int s = 0; s < p.n_seg; ++s) total += __ldcg(part + s);   // fixed order: deterministic
+    for (int s = 0; s < n_seg; ++s) total += __ldcg(part + s);     // fixed order: deterministic
     p.counter[lrow] = 0u;                                 // self-reset for the next launch
   }
   if (total == 0.0) total = CUDART_NAN;                   // lib:290
   p.vh[prof * p.n_freq + r] = total + rec.alt_min;        // lib:292
+}
+
+// Direct mode (large batches): tile = blockIdx.x, n_seg fixed by the host; rows without reflection exit.
+// Planned mode (small batches): K1 appended the rows that reflect to a compact list.  With few rows the
+// kernel is latency-bound unless only live rows get tiles and the segment count makes the live tiles fill
+// the resident-CTA slots, so every CTA sizes the tiling from the live-row count (same arithmetic in every
+// CTA, candidates prepared by the host) and strides over live_rows * n_seg tiles.
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  if (p.live_count == nullptr) {
+    const int64_t tile = blockIdx.x;
+    const int64_t lrow = tile / p.n_seg;
+    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
+    return;
+  }
+  const int live = (int)__ldcg(p.live_count);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.live_count_other = 0u;   // consumed by the previous call
+  // cost model: waves * (per-tile overhead + points per tile * cycles per point at full occupancy)
+  int n_seg = 1, seg_len = p.n_points;
+  {
+    float best_cost = 3.0e38f;
+    const float inv_slots = 1.0f / (float)p.slots;
+    for (int c = 0; c < p.n_cand; ++c) {
+      const float tiles = (float)max(live, 1) * (float)p.cand_seg[c];
+      const float waves = ceilf(tiles * inv_slots - 1e-4f);
+      const float cost = waves * ((float)kPlanTileOverhead + (float)p.cand_len[c] * (float)kPlanCyclesPerPoint);
+      if (cost < best_cost) { best_cost = cost; n_seg = p.cand_seg[c]; seg_len = p.cand_len[c]; }
+    }
+  }
+  const int n_tiles = live * n_seg;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int li = t / n_seg;
+    const LiveRow e = p.live_list[li];
+    tile_body<MODE, LITERAL>(p, e.row, e.span, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
+    __syncthreads();                                      // shared memory is reused by the next tile
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -821,13 +938,18 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
   return cudaGetLastError();
 }
 
+int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm) {
+  const int by_smem = (int)((size_t)max_smem_per_sm / (vfo_tile_smem_bytes(n_alt) + 1024));
+  return by_smem < kTileMinBlocks ? (by_smem < 1 ? 1 : by_smem) : kTileMinBlocks;
+}
+
 template <int MODE, bool LITERAL>
 static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
   const size_t smem = vfo_tile_smem_bytes(p.n_alt);
   auto kern = vfo_tile_kernel<MODE, LITERAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)n_tiles, kThreads, smem, stream>>>(p);
+  kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -6,7 +6,16 @@
 
 namespace prhf {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;                // K1 block size
+constexpr int kMaxWarps = 8;
+#ifndef PRHF_TILE_THREADS
+#define PRHF_TILE_THREADS 256
+#endif
+#ifndef PRHF_TILE_MINB
+#define PRHF_TILE_MINB 3
+#endif
+constexpr int kTileThreads = PRHF_TILE_THREADS;   // K2 block size (multiple of 64, <= 256)
+constexpr int kTileMinBlocks = PRHF_TILE_MINB;    // K2 resident CTAs per SM the register budget targets
 constexpr int kRowsPerCta = kThreads / 32;   // K1: one warp per sounding frequency
 constexpr int kMultPad = 4;                  // extra multiplier-table entries (value 1) past n_points
 
@@ -26,6 +35,17 @@ struct __align__(16) ProfileRecord {  // 64 bytes per profile, written by K1, re
   double sn0, cs0;                // sin / cos of the field angle at level 0 (all levels when kFlagPsiConst)
   double pad[2];
 };
+
+struct __align__(16) LiveRow {    // planned mode: one entry per row that reflects, appended by K1
+  int row;                        // row index inside the launch
+  int pad;
+  double span;                    // h_c - alt0
+};
+// planner cost model (SM cycles): per-tile prologue + reduction, and loop cycles per grid point of one
+// tile when the SM is fully occupied (measured with the developer phase trace, tools/trace_tiles.py)
+constexpr double kPlanTileOverhead = 2600.0;
+constexpr double kPlanCyclesPerPoint = 3.2;
+constexpr int kMaxPlanCand = 32;
 
 struct VfoParams {
   const double* freq;      // MHz; [n_freq] or per-profile rows
@@ -50,9 +70,21 @@ struct VfoParams {
   double* partial;         // [rows_in_launch x n_seg] when n_seg > 1
   unsigned* counter;       // [rows_in_launch], zero on entry, zero on exit
   long long* trace;        // developer phase trace [tiles x 8] (PRHF_TRACE builds), else null
+  // planned mode (small batches); null in direct mode
+  unsigned* live_count;        // zero on entry; K1 appends, K2 reads
+  unsigned* live_count_other;  // the other call parity's counter: K2 zeroes it for the next call
+  LiveRow* live_list;          // [rows_in_launch]
+  int64_t rows_in_launch;
+  int max_seg;             // stride of `partial` per row; planner's upper bound on n_seg
+  int slots;               // resident tile-kernel CTAs on the device
+  int n_cand;              // planner candidates: (segments per row, grid points per segment)
+  int cand_seg[kMaxPlanCand];
+  int cand_len[kMaxPlanCand];
+  long long* trace_k1;     // developer phase trace of K1 [ctas x 8] (PRHF_TRACE builds), else null
 };
 
 size_t vfo_smem_bytes(int n_alt);
+int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);

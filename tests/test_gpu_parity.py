@@ -253,3 +253,39 @@ def test_critical_frequency_ulp_sweep(vfo, golden, mode):
     # rows whose reflection level is a flat spot of the profile are ill-conditioned in h_c itself;
     # the mask must still agree exactly and the values to 1e-9 (X) / rounding ball (O)
     assert_parity(got, ref, tru, mode, "ulp sweep")
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_planned_mode_matches_direct_mode(vfo, golden, mode, monkeypatch):
+    """Small batches use K1's tile planner (adaptive segments, compact live-tile list); the result must
+    not depend on it.  PRHF_PLANNED_MAX_ROWS=0 forces the direct mode."""
+    from pyrayhf_b200 import _cabi
+    fx = golden.fixtures
+    args = (fx["freq_a"], fx["Night_den"], fx["Night_bmag"], fx["Night_bpsi"], fx["Night_alt"], mode, 20000)
+    planned = vfo.vertical_forward_operator(*args)
+    planned2 = vfo.vertical_forward_operator(*args)
+    assert np.array_equal(planned, planned2, equal_nan=True)          # self-resetting counters, determinism
+    monkeypatch.setenv("PRHF_PLANNED_MAX_ROWS", "0")
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    direct = vfo.vertical_forward_operator(*args)
+    assert np.array_equal(np.isnan(planned), np.isnan(direct))
+    assert rel_err(planned, direct) < 1e-13
+    assert_parity(planned, fx["ref_Night_%s_20000_a" % mode], fx["truth_Night_%s_20000_a" % mode], mode, "planned")
+    # a handful of profiles (still planned mode), incl. one failed profile and an all-dead one
+    monkeypatch.delenv("PRHF_PLANNED_MAX_ROWS")
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    lat, lon = synth.grid_subset(6, seed=5)
+    alt = synth.default_alt()
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    den[2, 3] = -1.0
+    den[4] *= 1e-6                                    # foF2 far below every sounding frequency
+    f = synth.default_freq()
+    got, st = vfo.vertical_forward_operator_batched(f, den, bmag, bpsi, alt, mode, 5000, errors='nan',
+                                                    return_status=True)
+    assert list(st) == [0, 0, 1, 0, 0, 0]
+    for p in (0, 1, 3, 4, 5):
+        ref = vfo_oracle.vertical_forward_operator(f, den[p], bmag[p], bpsi[p], alt, mode, 5000)
+        assert np.array_equal(np.isnan(got[p]), np.isnan(ref)), p
+        if mode == 'X':
+            assert rel_err(got[p], ref) < 1e-9
+    assert np.all(np.isnan(got[2]))

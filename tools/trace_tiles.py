@@ -33,8 +33,19 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush.zero_()
     pyrayhf_b200.vertical_forward_operator_batched(*t, 'X', 20000)
-    out = np.zeros((n_tiles, 8), dtype=np.int64)
+    out = np.zeros((n_tiles + 4096, 8), dtype=np.int64)
     L.prhf_debug_trace_read(ctx.handle, n_tiles, vp(out.ctypes.data))
+    k1 = out[n_tiles:]
+    k1 = k1[k1[:, 0] != 0]
+    out = out[:n_tiles]
+    print('K1 CTAs', len(k1))
+    for a, b, nm in ((0, 1, 'stage loads'), (1, 2, 'argmax/min'), (2, 3, 'checks/flags'), (3, 4, 'rows'), (4, 5, 'sync')):
+        d = k1[:, b] - k1[:, a]
+        print('  K1 %-12s cycles: median %6.0f max %6.0f' % (nm, np.median(d), d.max()))
+    last = k1[k1[:, 7] != 0]
+    if len(last):
+        print('  K1 planner (last CTA): wait->start %d, scan+plan %d cycles' % (last[0, 6] - last[0, 5], last[0, 7] - last[0, 6]))
+    print('  K1 CTA total median %d max %d' % (np.median(k1[:, 4] - k1[:, 0]), (k1[:, 4] - k1[:, 0]).max()))
     used = out[:, 1] != 0
     tr = out[used]
     live = tr[:, 7] != 0
