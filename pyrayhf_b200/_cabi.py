@@ -34,6 +34,11 @@ _u = ctypes.c_uint
 _lib = None
 _lock = threading.Lock()
 
+try:                                   # optional buffer-protocol caller (pyrayhf_b200/csrc/_fastcall.c)
+    from pyrayhf_b200 import _prhf_fast as _fast
+except ImportError:                    # same C-ABI call through ctypes instead
+    _fast = None
+
 
 class PrhfError(RuntimeError):
     """A C-ABI call failed (status code in ``.code``)."""
@@ -99,6 +104,10 @@ class Context:
         self._h = h
         self._L = L
         self.device = device
+        self.vfo_host = lambda *a, _f=L.prhf_vfo_host_f64, _h=h: _f(_h, *a)
+        self.fast = _fast
+        self.fn_addr = ctypes.cast(L.prhf_vfo_host_f64, ctypes.c_void_p).value
+        self.ctx_addr = h.value
 
     def close(self):
         if getattr(self, "_h", None):

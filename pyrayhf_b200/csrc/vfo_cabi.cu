@@ -12,12 +12,19 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <map>
 #include <mutex>
 #include <new>
 
 #include "../../include/pyrayhf_b200.h"
 #include "vfo_kernels.h"
+
+struct GraphEntry {                  // host entry: captured [H2D copy, K1, K2] per call shape
+  uint64_t epoch = 0;
+  int calls = 0;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};   // one per planned-mode call parity
+};
 
 struct prhf_ctx {
   int device = 0;
@@ -49,6 +56,10 @@ struct prhf_ctx {
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
   int plan_parity = 0;
+  // host entry graph cache; `epoch` changes whenever a device buffer baked into a graph is reallocated
+  uint64_t epoch = 1;
+  bool use_graphs = true;            // PRHF_NO_GRAPH=1 disables
+  std::map<std::array<int64_t, 9>, GraphEntry> graphs;
   int max_smem_per_sm = 0;
   int planned_max_rows = 4096;       // PRHF_PLANNED_MAX_ROWS
 };
@@ -107,6 +118,7 @@ int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
     ctx->prof_cap = 0;
     PRHF_CUDA(ctx, cudaMalloc(&ctx->prof_rec, sizeof(prhf::ProfileRecord) * n_prof));
     ctx->prof_cap = n_prof;
+    ctx->epoch++;
   }
   if (n_rows > ctx->row_cap) {
     if (ctx->row_span) cudaFree(ctx->row_span);
@@ -114,6 +126,7 @@ int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
     ctx->row_cap = 0;
     PRHF_CUDA(ctx, cudaMalloc(&ctx->row_span, sizeof(double) * n_rows));
     ctx->row_cap = n_rows;
+    ctx->epoch++;
   }
   return PRHF_OK;
 }
@@ -129,6 +142,7 @@ int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
     ctx->live_list_cap = 0;
     PRHF_CUDA(ctx, cudaMalloc(&ctx->live_list, sizeof(prhf::LiveRow) * n_rows));
     ctx->live_list_cap = n_rows;
+    ctx->epoch++;
   }
   return PRHF_OK;
 }
@@ -140,6 +154,7 @@ int ensure_workspace(prhf_ctx* ctx, size_t n_partial, size_t n_counter) {
     ctx->partial_cap = 0;
     PRHF_CUDA(ctx, cudaMalloc(&ctx->partial, sizeof(double) * n_partial));
     ctx->partial_cap = n_partial;
+    ctx->epoch++;
   }
   if (n_counter > ctx->counter_cap) {
     // A larger counter array replaces the old one; in-flight launches on the old array must finish.
@@ -150,6 +165,7 @@ int ensure_workspace(prhf_ctx* ctx, size_t n_partial, size_t n_counter) {
     PRHF_CUDA(ctx, cudaMalloc(&ctx->counter, sizeof(unsigned) * n_counter));
     PRHF_CUDA(ctx, cudaMemset(ctx->counter, 0, sizeof(unsigned) * n_counter));
     ctx->counter_cap = n_counter;
+    ctx->epoch++;
   }
   return PRHF_OK;
 }
@@ -174,6 +190,10 @@ void choose_tiling(const prhf_ctx* ctx, int64_t rows, int n_points, int* seg_len
   sl = std::max(sl, 1);
   *seg_len = sl;
   *n_seg = (n_points + sl - 1) / sl;
+}
+
+bool use_planned_mode(const prhf_ctx* ctx, int64_t rows_total, int n_points) {
+  return ctx->seg_len_override <= 0 && rows_total <= (int64_t)ctx->planned_max_rows && n_points >= 2048;
 }
 
 int validate(const prhf_ctx* ctx, const void* freq, int n_freq, const void* den, const void* bmag, const void* bpsi,
@@ -231,6 +251,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if (const char* s = getenv("PRHF_PLANNED_MAX_ROWS")) ctx->planned_max_rows = atoi(s);
+  if (const char* s = getenv("PRHF_NO_GRAPH")) ctx->use_graphs = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -246,6 +267,9 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
+  for (auto& kv : ctx->graphs)
+    for (int k = 0; k < 2; ++k)
+      if (kv.second.exec[k]) cudaGraphExecDestroy(kv.second.exec[k]);
   for (auto& kv : ctx->mult) cudaFree(kv.second);
   if (ctx->partial) cudaFree(ctx->partial);
   if (ctx->counter) cudaFree(ctx->counter);
@@ -314,8 +338,7 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
   // Small batches (fewer rows than a few waves of tiles): planned mode.  K1's last CTA counts the rows
   // that reflect and sizes the segments so that the live tiles fill the resident-CTA slots; K2 strides
   // over the compact tile list.  Large batches: direct mode, one tile per row.
-  const bool planned = ctx->seg_len_override <= 0 && rows_total <= (int64_t)ctx->planned_max_rows &&
-                       n_points >= 2048;
+  const bool planned = use_planned_mode(ctx, rows_total, n_points);
   int seg_len = 0, n_seg = 0;
   int n_cand = 0, cand_seg[prhf::kMaxPlanCand] = {0}, cand_len[prhf::kMaxPlanCand] = {0};
   if (planned) {
@@ -443,7 +466,12 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     PRHF_CUDA(ctx, cudaMalloc(&ctx->d_arena, need));
     PRHF_CUDA(ctx, cudaMallocHost(&ctx->h_arena, need));
     ctx->arena_cap = need;
+    ctx->epoch++;
   }
+  // Small calls (one chunk, outputs <= 1 MiB): the kernels write vh / status straight into the pinned host
+  // arena (zero-copy over PCIe, no D2H copy node) and the [H2D copy, K1, K2] sequence is replayed from a
+  // CUDA graph captured on the second call with the same shape.
+  const bool small = (chunk == n_profiles) && (vh_bytes + sizeof(int) * (size_t)chunk <= ((size_t)1 << 20));
   for (int64_t p0 = 0; p0 < n_profiles; p0 += chunk) {
     const int64_t np = std::min(chunk, n_profiles - p0);
     size_t off = 0;
@@ -465,17 +493,70 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     const size_t o_den = put(den + p0 * n_alt, n_alt, (size_t)n_alt, np);
     const size_t o_b = put(bmag + p0 * n_alt, n_alt, (size_t)n_alt, np);
     const size_t o_psi = put(bpsi + p0 * n_alt, n_alt, (size_t)n_alt, np);
-    PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, off, cudaMemcpyHostToDevice, ctx->stream));
-    double* d_vh = (double*)(ctx->d_arena + out_off);
-    int* d_st = (int*)(ctx->d_arena + out_off + d8 * (size_t)n_freq * np);
-    rc = prhf_vfo_f64(ctx, (const double*)(ctx->d_arena + o_freq), n_freq, freq_shared ? 0 : n_freq,
-                      (const double*)(ctx->d_arena + o_den), (const double*)(ctx->d_arena + o_b),
-                      (const double*)(ctx->d_arena + o_psi), (const double*)(ctx->d_arena + o_alt),
-                      alt_shared ? 0 : n_alt, np, n_alt, mode, n_points, flags, d_vh, d_st, ctx->stream);
-    if (rc != PRHF_OK) return rc;
+    char* out_base = small ? ctx->h_arena : ctx->d_arena;       // pinned host memory is device-addressable (UVA)
+    double* d_vh = (double*)(out_base + out_off);
+    int* d_st = (int*)(out_base + out_off + d8 * (size_t)n_freq * np);
+    auto enqueue = [&]() -> int {
+      PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, off, cudaMemcpyHostToDevice, ctx->stream));
+      return prhf_vfo_f64(ctx, (const double*)(ctx->d_arena + o_freq), n_freq, freq_shared ? 0 : n_freq,
+                          (const double*)(ctx->d_arena + o_den), (const double*)(ctx->d_arena + o_b),
+                          (const double*)(ctx->d_arena + o_psi), (const double*)(ctx->d_arena + o_alt),
+                          alt_shared ? 0 : n_alt, np, n_alt, mode, n_points, flags, d_vh, d_st, ctx->stream);
+    };
+    bool done = false;
+    if (small && ctx->use_graphs) {
+      const std::array<int64_t, 9> key = {n_freq, freq_shared, alt_shared, np, n_alt, mode, n_points, (int64_t)flags,
+                                          ctx->seg_len_override};
+      GraphEntry& ge = ctx->graphs[key];
+      if (ge.epoch != ctx->epoch) {                           // buffers moved since capture: start over
+        for (int k = 0; k < 2; ++k)
+          if (ge.exec[k]) { cudaGraphExecDestroy(ge.exec[k]); ge.exec[k] = nullptr; }
+        ge.calls = 0;
+      }
+      const bool planned = use_planned_mode(ctx, np * (int64_t)n_freq, n_points);
+      const int parity = planned ? ctx->plan_parity : 0;
+      if (ge.calls >= 1) {
+        if (!ge.exec[parity]) {
+          cudaGraph_t graph = nullptr;
+          if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const int64_t launches0 = ctx->launches;
+            rc = enqueue();                                    // flips plan_parity when planned
+            ctx->launches = launches0;
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc == PRHF_OK && ce == cudaSuccess && graph &&
+                cudaGraphInstantiate(&ge.exec[parity], graph, 0) != cudaSuccess)
+              ge.exec[parity] = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+            if (planned) ctx->plan_parity = parity;            // the captured call has not run yet
+          }
+          if (!ge.exec[parity]) {                              // capture is an optimisation, never a requirement
+            cudaGetLastError();
+            ctx->use_graphs = false;
+          }
+        }
+        if (ge.exec[parity]) {
+          PRHF_CUDA(ctx, cudaGraphLaunch(ge.exec[parity], ctx->stream));
+          if (planned) ctx->plan_parity ^= 1;
+          ctx->launches += 2;
+          done = true;
+        }
+      }
+      if (!done) {
+        rc = enqueue();
+        if (rc != PRHF_OK) return rc;
+        ge.calls++;
+        ge.epoch = ctx->epoch;
+        done = true;
+      }
+    }
+    if (!done) {
+      rc = enqueue();
+      if (rc != PRHF_OK) return rc;
+    }
     const size_t out_bytes = d8 * (size_t)n_freq * np + sizeof(int) * (size_t)np;
-    PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->h_arena + out_off, ctx->d_arena + out_off, out_bytes, cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    if (!small)
+      PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->h_arena + out_off, ctx->d_arena + out_off, out_bytes, cudaMemcpyDeviceToHost,
+                                     ctx->stream));
     PRHF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(vh_out + p0 * n_freq, ctx->h_arena + out_off, d8 * (size_t)n_freq * np);
     if (status) memcpy(status + p0, ctx->h_arena + out_off + d8 * (size_t)n_freq * np, sizeof(int) * (size_t)np);

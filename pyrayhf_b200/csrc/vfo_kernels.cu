@@ -928,9 +928,22 @@ size_t vfo_smem_bytes(int n_alt) {
   return a > b ? a : b;
 }
 
+// cudaFuncSetAttribute costs ~1-2 us of host time per call; remember the largest size already granted per
+// (device, kernel) so that steady-state launches skip it (also keeps it out of stream capture).
+static cudaError_t grant_dynamic_smem(const void* func, int slot, size_t smem) {
+  static size_t granted[64][8] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (smem <= granted[dev][slot]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) granted[dev][slot] = smem;
+  return e;
+}
+
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream) {
   const size_t smem = vfo_rows_smem_bytes(p.n_alt);
-  cudaError_t e = cudaFuncSetAttribute(vfo_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = grant_dynamic_smem((const void*)vfo_rows_kernel, 0, smem);
   if (e != cudaSuccess) return e;
   const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
@@ -947,7 +960,7 @@ template <int MODE, bool LITERAL>
 static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
   const size_t smem = vfo_tile_smem_bytes(p.n_alt);
   auto kern = vfo_tile_kernel<MODE, LITERAL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 1 + MODE * 2 + (LITERAL ? 1 : 0), smem);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
   return cudaGetLastError();

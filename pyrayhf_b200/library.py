@@ -21,7 +21,7 @@ def _logger():
     return pyrayhf_b200.logger
 
 
-def _mode_code(mode):
+def _mode_code(mode):  # noqa: E302
     # library.py:391-396: exact, case-sensitive comparison with 'O' / 'X'
     if isinstance(mode, str) and mode == 'O':
         return 0
@@ -45,6 +45,17 @@ def _raise_profile_status(st):
         raise IndexError("index -1 is out of bounds for axis 1 with size 0")  # library.py:399
 
 
+_F64 = np.dtype(np.float64)
+_status_buf = {}
+
+
+def _vec(a):
+    """float64, C-contiguous, 1-D view/copy of ``a`` (fast path: already in that form)."""
+    if type(a) is np.ndarray and a.dtype == _F64 and a.ndim == 1 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+
+
 def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
                               literal=False, device=-1):
     """Calculate virtual height from ionosonde freq and ion profile (drop-in).
@@ -59,22 +70,38 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
     ``literal=True`` evaluates the Appleton-Hartree block in the reference's operation
     order (debug aid; O-mode then inherits the reference's cancellation noise).
     """
-    freq = np.asarray(freq)
-    den, bmag, bpsi, alt = (np.asarray(v) for v in (den, bmag, bpsi, alt))
-    # library.py:487-488: chained inequality, logs and continues
-    if den.shape != bmag.shape != bpsi.shape != alt.shape:
-        _logger().error("Error: freq, den, bmag, bpsi, alt should have same size")
-    code = _mode_code(mode)
-    if freq.ndim > 1:
+    if mode == 'O':                         # library.py:391-396: exact, case-sensitive
+        code = 0
+    elif mode == 'X':
+        code = 1
+    else:
+        raise ValueError("mode must be 'O' or 'X'")
+    n_points = int(n_points)
+    ctx = _cabi.context(device)
+    st = _status_buf.get(ctx)
+    if st is None:
+        st = _status_buf[ctx] = np.zeros(1, dtype=np.int32)
+    flags = _cabi.FLAG_LITERAL if literal else 0
+    fast = ctx.fast
+    if fast is not None and n_points >= 1 and type(freq) is np.ndarray and freq.ndim == 1:
+        # float64 contiguous vectors go straight to the C ABI through the buffer-protocol shim
+        vh = np.empty(freq.shape[0], dtype=np.float64)
+        rc = fast.vfo_host(ctx.fn_addr, ctx.ctx_addr, freq, den, bmag, bpsi, alt, code, n_points, flags, vh, st)
+        if rc == 0:
+            if st[0]:
+                _raise_profile_status(int(st[0]))
+            return vh
+        if rc > 0:
+            ctx.check(rc)
+    if np.ndim(freq) > 1:
         raise ValueError("operands could not be broadcast together: freq must be 0-d or 1-d")
-    out_shape = (freq.size,)
-    f = _f64(freq).reshape(-1)
-    d, b, p, a = _f64(den).reshape(-1), _f64(bmag).reshape(-1), _f64(bpsi).reshape(-1), _f64(alt).reshape(-1)
+    f, d, b, p, a = _vec(freq), _vec(den), _vec(bmag), _vec(bpsi), _vec(alt)
     n_alt = d.size
     if not (b.size == p.size == a.size == n_alt):
+        # library.py:487-488 only logs a shape mismatch and then fails inside numpy; there is no
+        # meaningful result to reproduce for ragged inputs
+        _logger().error("Error: freq, den, bmag, bpsi, alt should have same size")
         raise ValueError("den, bmag, bpsi, alt must have the same length")
-    n_points = int(n_points)
-    vh = np.empty(f.size, dtype=np.float64)
     if n_alt == 0:
         raise ValueError("attempt to get argmax of an empty sequence")       # np.argmax, library.py:371
     if f.size == 0:
@@ -83,14 +110,14 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
     if n_points < 1:
         # np.nanmax of an empty [F x 0] array at library.py:201
         raise ValueError("zero-size array to reduction operation fmax which has no identity")
-    ctx = _cabi.context(device)
-    st = np.zeros(1, dtype=np.int32)
-    rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(f), f.size, 0, _ptr(d), _ptr(b), _ptr(p), _ptr(a), 0,
-                                   1, n_alt, code, n_points, _cabi.FLAG_LITERAL if literal else 0,
-                                   _ptr(vh), _ptr(st))
-    ctx.check(rc)
-    _raise_profile_status(int(st[0]))
-    return vh.reshape(out_shape)
+    vh = np.empty(f.size, dtype=np.float64)
+    rc = ctx.vfo_host(f.ctypes.data, f.size, 0, d.ctypes.data, b.ctypes.data, p.ctypes.data, a.ctypes.data, 0,
+                      1, n_alt, code, n_points, flags, vh.ctypes.data, st.ctypes.data)
+    if rc:
+        ctx.check(rc)
+    if st[0]:
+        _raise_profile_status(int(st[0]))
+    return vh
 
 
 def _is_torch_tensor(x):
