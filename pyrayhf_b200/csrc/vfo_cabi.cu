@@ -24,6 +24,7 @@ struct GraphEntry {                  // host entry: captured [H2D copy, K1, K2] 
   uint64_t epoch = 0;
   int calls = 0;
   cudaGraphExec_t exec[2] = {nullptr, nullptr};   // one per planned-mode call parity
+  int n_launches = 0;                              // kernels inside one replay
 };
 
 struct prhf_ctx {
@@ -52,7 +53,9 @@ struct prhf_ctx {
   long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
   size_t trace_k1_off = 0;           // K1 entries start here (in long longs)
   // planned mode (small batches): tile plan, compact tile list, K1 completion counter
-  unsigned* live_count = nullptr;    // [2], one per call parity
+  unsigned* live_count = nullptr;    // [2] one per call parity, followed by the fused kernel's barrier words [2]
+  bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
+  bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
   int plan_parity = 0;
@@ -133,8 +136,8 @@ int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
 
 int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
   if (!ctx->live_count) {
-    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_count, 2 * sizeof(unsigned)));
-    PRHF_CUDA(ctx, cudaMemset(ctx->live_count, 0, 2 * sizeof(unsigned)));
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_count, 4 * sizeof(unsigned)));
+    PRHF_CUDA(ctx, cudaMemset(ctx->live_count, 0, 4 * sizeof(unsigned)));
   }
   if (n_rows > ctx->live_list_cap) {
     if (ctx->live_list) cudaFree(ctx->live_list);
@@ -252,6 +255,8 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   ctx->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if (const char* s = getenv("PRHF_PLANNED_MAX_ROWS")) ctx->planned_max_rows = atoi(s);
   if (const char* s = getenv("PRHF_NO_GRAPH")) ctx->use_graphs = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_FUSED")) ctx->use_fused = (atoi(s) != 0);
+  if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -413,17 +418,32 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
       P.live_count = ctx->live_count + ctx->plan_parity;
       P.live_count_other = ctx->live_count + (1 - ctx->plan_parity);
       P.live_list = ctx->live_list;
+      P.grid_bar = ctx->live_count + 2;
       ctx->plan_parity ^= 1;
     } else {
       P.live_count = P.live_count_other = nullptr;
       P.live_list = nullptr;
+      P.grid_bar = nullptr;
     }
     P.rows_in_launch = np * n_freq;
+    P.use_pdl = ctx->use_pdl ? 1 : 0;
     P.max_seg = n_seg;
     P.slots = slots;
     P.n_cand = n_cand;
     for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
+    if (planned && ctx->use_fused) {
+      // one cooperative launch: row setup, grid barrier, tiles
+      const int rows_per_cta = prhf::kRowsPerCta * rows_per_warp;
+      const int64_t n_items = np * ((n_freq + rows_per_cta - 1) / rows_per_cta);
+      cudaError_t fe = prhf::launch_vfo_fused(P, mode, literal, (int)n_items, 1 << 20, ctx->sm_count, stream);
+      if (fe == cudaSuccess) {
+        ctx->launches += 1;
+        continue;
+      }
+      cudaGetLastError();
+      ctx->use_fused = false;                                 // e.g. cooperative launch unsupported: two launches
+    }
     PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
     // planned mode: enough CTAs for two waves of slots; they stride over however many tiles K1 planned
     const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots) : np * tiles_per_profile;
@@ -521,6 +541,7 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
           if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
             const int64_t launches0 = ctx->launches;
             rc = enqueue();                                    // flips plan_parity when planned
+            ge.n_launches = (int)(ctx->launches - launches0);
             ctx->launches = launches0;
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
             if (rc == PRHF_OK && ce == cudaSuccess && graph &&
@@ -537,7 +558,7 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
         if (ge.exec[parity]) {
           PRHF_CUDA(ctx, cudaGraphLaunch(ge.exec[parity], ctx->stream));
           if (planned) ctx->plan_parity ^= 1;
-          ctx->launches += 2;
+          ctx->launches += ge.n_launches;
           done = true;
         }
       }

@@ -203,6 +203,58 @@ __device__ __forceinline__ double ah_core(double X, double Y, double sn, double 
   return (mu <= 1.0) ? mup : CUDART_NAN;               // lib:233 (NaN mu) and lib:238
 }
 
+// ---- hot-loop form of ah_core ----
+// Inputs: YTh = Y sin(psi) / sqrt(2) (so that a = YTh^2), YL = Y cos(psi).  Returns mu' and mu; the caller
+// tests validity (mu <= 1, not NaN) on the bit patterns with integer instructions, keeping compares off the
+// FP64 pipe.  36 (X) / 37 (O) FP64 instructions.
+template <int MODE>
+__device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double* mu_out) {
+  const double Xm1 = 1.0 - X;
+  const double a = YTh * YTh;
+  const double w = (YL * YL) * Xm1;
+  const double a2 = a * a;
+  const double alpha = fma(w, Xm1, a2);
+  const double rb = rsqrt_fast(alpha);
+  const double beta = alpha * rb;
+  const double P = a + beta;
+  const double T = fma(a2, rb, beta);                   // beta + a^2 / beta
+  double mu, c, q, dDdX, hYd;                           // hYd = (Y dD/dY) / 2
+  if (MODE == 1) {
+    const double D = Xm1 - P;
+    const double XX = X * Xm1;
+    const double E = D - XX;
+    const double rs = rsqrt_fast(D * E);
+    const double t1 = E * rs;
+    mu = fabs(t1);
+    q = XX * (t1 * rs);
+    c = copysign(rs, t1);
+    dDdX = fma(w, rb, -1.0);
+    hYd = fma(-0.5, T, -a);
+  } else {
+    const double N = fma(Xm1, P, w);
+    const double G = P + w;
+    const double z = Xm1 * N;
+    const double rs = rsqrt_fast(z * (Xm1 * G));
+    const double v = z * rs;
+    mu = fabs(v);
+    q = (X * P) * (v * (Xm1 * rs));
+    c = P * rs;
+    dDdX = -fma(w, rb, 1.0);
+    hYd = fma(0.5, T, -a);
+  }
+  const double br = fma(q, hYd, X * fma(q, dDdX, fma(2.0, X, -1.0)));
+  *mu_out = mu;
+  return fma(-c, br, mu);
+}
+
+// mu' is kept when the reference keeps it: mu not NaN (lib:233), mu <= 1 (lib:238), mu' itself not NaN
+// (nansum, lib:288).  Integer tests on the IEEE bit patterns (mu >= 0 by construction).
+__device__ __forceinline__ bool keep_term(double mu, double mup) {
+  const unsigned long long mb = (unsigned long long)__double_as_longlong(mu);
+  const unsigned long long pb = (unsigned long long)__double_as_longlong(mup) & 0x7fffffffffffffffULL;
+  return (mb <= 0x3ff0000000000000ULL) && (pb <= 0x7ff0000000000000ULL);
+}
+
 // sin/cos of (r_k + delta) from the node's sin/cos and a short Taylor series in delta (|delta| <= 0.05:
 // truncation < 6e-18).  Replaces a full-range sincos per grid point.
 __device__ __forceinline__ void rotate_sincos(double sk, double ck, double delta, double* sn, double* cs) {

@@ -233,9 +233,9 @@ __device__ __forceinline__ int bracket_in(double x, const double* xp, int lo, in
 // ==========================================================================================
 // K1: per-row setup
 // ==========================================================================================
-__global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, const int mode) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ BlockScratch sc;
+// `item` = (profile index inside the launch) * chunks + chunk of sounding frequencies.
+__device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, const int64_t item, double* smem,
+                                          BlockScratch& sc) {
   const int A = p.n_alt;
   double* s_den = smem;
   double* s_alt = s_den + A;
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
-  const int64_t lprof = blockIdx.x / chunks;            // profile index inside this launch
-  const int g = (int)(blockIdx.x % chunks);
+  const int64_t lprof = item / chunks;                  // profile index inside this launch
+  const int g = (int)(item % chunks);
   const int64_t prof = p.profile_offset + lprof;
 
   const double* g_den = p.den + prof * A;
@@ -256,6 +256,9 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
   const double* g_alt = p.alt + prof * p.alt_stride;
 
   PRHF_TRACE_K1(0);
+#ifdef PRHF_TRACE
+  if (p.trace_k1 && threadIdx.x == 0) p.trace_k1[(size_t)blockIdx.x * 8 + 6] = trace_globaltimer();
+#endif
   // ---- stage the whole profile with all loads in flight at once (one DRAM latency), then
   //      argmax(den) (lib:371) and min(alt) (lib:507) ----
   double best_v = -CUDART_INF;
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     if (!(((d - d) + (b - b)) + ((ps - ps) + (a - a)) == 0.0)) chk |= 2;
     bmax = fmax(bmax, fabs(b));
     if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 0.25 * mean_step)) chk |= 4;
+    if (!(a > 0.0)) chk |= 2;                           // the fast paths compare altitudes as integers
     if (k + 1 < nt) {
       if (!(__dsub_rn(s_alt[k + 1], a) > 0.0)) chk |= 2;
       const double step = fabs(__dsub_rn(s_psi[k + 1], ps)) * kDeg2Rad;
@@ -483,6 +487,18 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
     __syncwarp();
   }
   PRHF_TRACE_K1(4);
+#ifdef PRHF_TRACE
+  if (p.trace_k1 && threadIdx.x == 0) p.trace_k1[(size_t)blockIdx.x * 8 + 7] = trace_globaltimer();
+#endif
+}
+
+__global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, const int mode) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ BlockScratch sc;
+  // Programmatic dependent launch: the tile kernel may be scheduled as soon as every CTA of this grid has
+  // started; it blocks in griddepcontrol.wait until this grid has completed and its writes are visible.
+  asm volatile("griddepcontrol.launch_dependents;");
+  rows_body(p, mode, blockIdx.x, smem, sc);
 }
 
 // ==========================================================================================
@@ -635,6 +651,94 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
   return acc0 + acc1;
 }
 
+// ---- hot loop of the fast paths ----
+// Differences from tile_sum: altitudes are positive on these paths (K1 flag), so brackets are tested on the
+// IEEE bit patterns with integer compares; h_i = fma(m_i, span, alt0) (<= 0.5 ulp from the reference's
+// multiply-then-add, lib:413); validity tests are integer; terms enter the sum through one FMA.
+__device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int jlo, int jhi, int guess) {
+  int j = min(max(guess, jlo), jhi);
+  const long long hb = __double_as_longlong(h);
+  const long long* alt = reinterpret_cast<const long long*>(&nodes[0].alt) - (ptrdiff_t)jlo * 8;
+  if (hb < alt[(ptrdiff_t)j * 8]) {
+    if (j == jlo) return jlo;                                // (rows on this path never fall below level jlo)
+    --j;
+    if (hb >= alt[(ptrdiff_t)j * 8]) return j;
+    return max(bracket_in<8>(h, &nodes[0].alt - (ptrdiff_t)jlo * 8, jlo, j - 1), jlo);
+  }
+  if (j == jhi || hb < alt[(ptrdiff_t)(j + 1) * 8]) return j;
+  ++j;
+  if (j == jhi || hb < alt[(ptrdiff_t)(j + 1) * 8]) return j;
+  return bracket_in<8>(h, &nodes[0].alt - (ptrdiff_t)jlo * 8, j + 1, jhi);
+}
+
+template <int MODE, int PATH>
+__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, int jlo, double* mu_out) {
+  const Node& nd = nodes[j - jlo];
+  const double t = h - nd.alt;
+  const double X = fma(nd.sx, t, nd.x);
+  if (PATH == kPathFast0) {
+    // node fields: y = Y sin(psi)/sqrt(2), sy its slope; srad = Y cos(psi), sn = its slope
+    return ah_hot<MODE>(X, fma(nd.sy, t, nd.y), fma(nd.sn, t, nd.srad), mu_out);
+  }
+  const double Y = fma(nd.sy, t, nd.y);
+  double sn, cs;
+  if (PATH == kPathFastS) rotate_sincos_small(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
+  else rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
+  return ah_hot<MODE>(X, (Y * sn) * 0.70710678118654752, Y * cs, mu_out);
+}
+
+// Branch-free bracket for altitude grids K1 flagged uniform (every level within a quarter step of
+// alt0 + k * mean step): floor((h - alt0) / step) is the bracket or one off, two integer compares decide.
+__device__ __forceinline__ int bracket_uniform(double h, const Node* nodes, int jlo, int jhi, int guess) {
+  const int j = min(max(guess, jlo), jhi - 1);                        // jhi > jlo on this path
+  const long long hb = __double_as_longlong(h);
+  const long long* alt = reinterpret_cast<const long long*>(&nodes[0].alt) + (ptrdiff_t)(j - jlo) * 8;
+  const int down = (hb < alt[0]) ? 1 : 0;
+  const int up = (hb >= alt[8]) ? 1 : 0;
+  return max(j + up - down, jlo);
+}
+
+template <int MODE, int PATH, bool UNIFORM>
+__device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                int i0, int i1, int n_points) {
+  double acc0 = 0.0, acc1 = 0.0;
+  const double2* m2 = reinterpret_cast<const double2*>(m);
+  const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
+  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kTileThreads) {
+    const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
+    const double mn = __ldg(m + i + 2);
+    const double h0 = fma(mm.x, rc.span, rc.alt0);                   // lib:413
+    const double h1 = fma(mm.y, rc.span, rc.alt0);
+    const double h2 = fma(mn, rc.span, rc.alt0);
+    double dh0 = h1 - h0, dh1 = h2 - h1;                             // lib:415
+    if (i == n_points - 1) dh0 = kBackoff;                           // lib:416
+    if (i + 1 == n_points - 1) dh1 = kBackoff;
+    int j0, j1;
+    if (UNIFORM) {
+      j0 = bracket_uniform(h0, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
+      j1 = bracket_uniform(h1, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.y * c1));
+    } else {
+      j0 = find_bracket_pos(h0, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
+      j1 = find_bracket_pos(h1, nodes, rc.jlo, rc.jhi, j0);
+    }
+    double mu0, mu1;
+    const double p0 = fast_point<MODE, PATH>(h0, j0, nodes, rc.jlo, &mu0);
+    const double p1 = fast_point<MODE, PATH>(h1, j1, nodes, rc.jlo, &mu1);
+    acc0 = fma(keep_term(mu0, p0) ? p0 : 0.0, dh0, acc0);            // nansum (lib:288)
+    acc1 = fma((keep_term(mu1, p1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
+  }
+  return acc0 + acc1;
+}
+
+// ProfileRecord through L2 (ld.cg): in the fused kernel it was written by another CTA of the same launch.
+__device__ __forceinline__ ProfileRecord load_profile_record(const ProfileRecord* ptr) {
+  union { ProfileRecord r; int4 v[4]; } u;
+  const int4* src = reinterpret_cast<const int4*>(ptr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) u.v[k] = __ldcg(src + k);
+  return u.r;
+}
+
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span, const int seg,
@@ -654,7 +758,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int i0 = seg * seg_len;
   const int i1 = min(p.n_points, i0 + seg_len);
   // every load of the prologue is independent of the others: issue them together
-  const ProfileRecord rec = p.prof_rec[lprof];
+  const ProfileRecord rec = load_profile_record(p.prof_rec + lprof);
   const double f_mhz = p.freq[prof * p.freq_stride + r];
   const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
   if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
@@ -733,8 +837,14 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
       nd.sy = ((b1 - b0) * ky) * inv_dx;
       nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
       if (path == kPathFast0) {
-        nd.sn = rec.sn0;
-        nd.cs = rec.cs0;
+        // constant field angle: interpolate YTh = Y sin(psi)/sqrt(2) and YL = Y cos(psi) directly
+        const double sh = rec.sn0 * 0.70710678118654752, cc = rec.cs0;
+        const double y0 = nd.y, sy0 = nd.sy;
+        nd.y = y0 * sh;
+        nd.sy = sy0 * sh;
+        nd.srad = y0 * cc;
+        nd.sn = sy0 * cc;
+        nd.cs = 0.0;
       } else {
         sincos(p0 * kDeg2Rad, &nd.sn, &nd.cs);
       }
@@ -774,12 +884,18 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
       }
     }
     acc = tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
-  } else if (path == kPathFast0) {
-    acc = tile_sum<MODE, kPathFast0, false>(nodes, rc, m, i0, i1, np, 0.0);
-  } else if (path == kPathFastS) {
-    acc = tile_sum<MODE, kPathFastS, false>(nodes, rc, m, i0, i1, np, 0.0);
-  } else if (path == kPathFastL) {
-    acc = tile_sum<MODE, kPathFastL, false>(nodes, rc, m, i0, i1, np, 0.0);
+  } else if (fast) {
+    // uniform grids with more than one staged level take the branch-free bracket
+    const bool uni = (rec.flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
+    if (path == kPathFast0)
+      acc = uni ? tile_sum_fast<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np)
+                : tile_sum_fast<MODE, kPathFast0, false>(nodes, rc, m, i0, i1, np);
+    else if (path == kPathFastS)
+      acc = uni ? tile_sum_fast<MODE, kPathFastS, true>(nodes, rc, m, i0, i1, np)
+                : tile_sum_fast<MODE, kPathFastS, false>(nodes, rc, m, i0, i1, np);
+    else
+      acc = uni ? tile_sum_fast<MODE, kPathFastL, true>(nodes, rc, m, i0, i1, np)
+                : tile_sum_fast<MODE, kPathFastL, false>(nodes, rc, m, i0, i1, np);
   } else if (path == kPathIso) {
     acc = tile_sum<MODE, kPathIso, false>(nodes, rc, m, i0, i1, np, 0.0);
   } else if (LITERAL) {
@@ -792,6 +908,9 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   PRHF_TRACE_MARK(6);
   const double s_tile = block_sum(acc, sc);
   PRHF_TRACE_MARK(7);
+#ifdef PRHF_TRACE
+  if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 8 + 0] |= (trace_globaltimer() << 10);
+#endif
   if (tid != 0) return;
   double total = s_tile;
   if (n_seg > 1) {
@@ -815,15 +934,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 // the resident-CTA slots, so every CTA sizes the tiling from the live-row count (same arithmetic in every
 // CTA, candidates prepared by the host) and strides over live_rows * n_seg tiles.
 template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(const VfoParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ BlockScratch sc;
-  if (p.live_count == nullptr) {
-    const int64_t tile = blockIdx.x;
-    const int64_t lrow = tile / p.n_seg;
-    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
-    return;
-  }
+__device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char* smem_raw, BlockScratch& sc) {
   const int live = (int)__ldcg(p.live_count);
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.live_count_other = 0u;   // consumed by the previous call
   // cost model: waves * (per-tile overhead + points per tile * cycles per point at full occupancy)
@@ -841,10 +952,61 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
   const int n_tiles = live * n_seg;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int li = t / n_seg;
-    const LiveRow e = p.live_list[li];
-    tile_body<MODE, LITERAL>(p, e.row, e.span, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
+    // written earlier in this launch sequence (possibly in this very kernel): bypass L1
+    const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
+    const double span = __hiloint2double(raw.w, raw.z);
+    tile_body<MODE, LITERAL>(p, raw.x, span, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
     __syncthreads();                                      // shared memory is reused by the next tile
   }
+}
+
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the row-setup grid has completed (no-op without PDL)
+  if (p.live_count == nullptr) {
+    const int64_t tile = blockIdx.x;
+    const int64_t lrow = tile / p.n_seg;
+    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
+    return;
+  }
+  planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
+}
+
+// Fused form of the planned mode (small batches), launched cooperatively with one wave of CTAs: the row
+// setup (K1) and the tiles (K2) run in ONE kernel separated by a grid-wide barrier, which removes the
+// second launch and the inter-kernel drain/fill from the latency-critical single-profile path.
+// The barrier is sense-reversing on two words in global memory (arrive count, generation): it resets
+// itself, so the same captured graph can replay the launch.
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* vgen = bar + 1;
+    const unsigned gen = *vgen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*vgen == gen) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_fused_kernel(const VfoParams p, const int n_items) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    rows_body(p, MODE, item, reinterpret_cast<double*>(smem_raw), sc);
+    __syncthreads();
+  }
+  grid_barrier(p.grid_bar);
+  planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -962,13 +1124,55 @@ static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_
   auto kern = vfo_tile_kernel<MODE, LITERAL>;
   cudaError_t e = grant_dynamic_smem((const void*)kern, 1 + MODE * 2 + (LITERAL ? 1 : 0), smem);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  if (!p.use_pdl) {
+    kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_tiles);
+  cfg.blockDim = dim3(kTileThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream) {
   if (mode == 0) return literal ? launch_tiles<0, true>(p, n_tiles, stream) : launch_tiles<0, false>(p, n_tiles, stream);
   return literal ? launch_tiles<1, true>(p, n_tiles, stream) : launch_tiles<1, false>(p, n_tiles, stream);
+}
+
+template <int MODE, bool LITERAL>
+static cudaError_t launch_fused_t(const VfoParams& p, int n_items, int max_grid, int sm_count, cudaStream_t stream) {
+  static_assert(kTileThreads == kThreads, "the fused kernel runs the row setup with the tile kernel's block size");
+  const size_t smem = vfo_smem_bytes(p.n_alt);
+  auto kern = vfo_fused_kernel<MODE, LITERAL>;
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 5 + MODE * 2 + (LITERAL ? 1 : 0), smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
+  if (e != cudaSuccess) return e;
+  int grid = per_sm * sm_count;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) return cudaErrorCooperativeLaunchTooLarge;
+  VfoParams pc = p;
+  pc.slots = grid;                                        // the planner sizes tiles for the CTAs that exist
+  int items = n_items;
+  void* args[] = {(void*)&pc, (void*)&items};
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kTileThreads), args, smem, stream);
+}
+
+cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
+                             cudaStream_t stream) {
+  if (mode == 0)
+    return literal ? launch_fused_t<0, true>(p, n_items, max_grid, sm_count, stream)
+                   : launch_fused_t<0, false>(p, n_items, max_grid, sm_count, stream);
+  return literal ? launch_fused_t<1, true>(p, n_items, max_grid, sm_count, stream)
+                 : launch_fused_t<1, false>(p, n_items, max_grid, sm_count, stream);
 }
 
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream) {

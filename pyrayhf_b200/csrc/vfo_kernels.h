@@ -75,6 +75,8 @@ struct VfoParams {
   unsigned* live_count_other;  // the other call parity's counter: K2 zeroes it for the next call
   LiveRow* live_list;          // [rows_in_launch]
   int64_t rows_in_launch;
+  int use_pdl;                 // launch the tile kernel with programmatic stream serialization
+  unsigned* grid_bar;          // fused kernel: {arrive count, generation}, both self-maintaining
   int max_seg;             // stride of `partial` per row; planner's upper bound on n_seg
   int slots;               // resident tile-kernel CTAs on the device
   int n_cand;              // planner candidates: (segments per row, grid points per segment)
@@ -87,6 +89,8 @@ size_t vfo_smem_bytes(int n_alt);
 int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
+cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
+                             cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);

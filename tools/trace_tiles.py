@@ -39,18 +39,21 @@ def main():
     k1 = k1[k1[:, 0] != 0]
     out = out[:n_tiles]
     print('K1 CTAs', len(k1))
-    for a, b, nm in ((0, 1, 'stage loads'), (1, 2, 'argmax/min'), (2, 3, 'checks/flags'), (3, 4, 'rows'), (4, 5, 'sync')):
+    k1_t0 = k1[:, 6].min()
+    print('  K1 start spread %.2f us, K1 last end at %.2f us after first start' % ((k1[:, 6].max() - k1_t0) / 1e3, (k1[:, 7].max() - k1_t0) / 1e3))
+    for a, b, nm in ((0, 1, 'stage loads'), (1, 2, 'argmax/min'), (2, 3, 'checks/flags'), (3, 4, 'rows')):
         d = k1[:, b] - k1[:, a]
         print('  K1 %-12s cycles: median %6.0f max %6.0f' % (nm, np.median(d), d.max()))
-    last = k1[k1[:, 7] != 0]
-    if len(last):
-        print('  K1 planner (last CTA): wait->start %d, scan+plan %d cycles' % (last[0, 6] - last[0, 5], last[0, 7] - last[0, 6]))
     print('  K1 CTA total median %d max %d' % (np.median(k1[:, 4] - k1[:, 0]), (k1[:, 4] - k1[:, 0]).max()))
     used = out[:, 1] != 0
     tr = out[used]
     live = tr[:, 7] != 0
     print("tiles launched", used.sum(), "live", live.sum())
     g0 = tr[:, 1].min()
+    gt_end = tr[:, 0] >> 10
+    tr[:, 0] &= 1023
+    print("tile starts: first %.2f us, last %.2f us after K1 first start; last tile end %.2f us" % (
+        (tr[:, 1].min() - k1_t0) / 1e3, (tr[:, 1].max() - k1_t0) / 1e3, (gt_end[gt_end > 0].max() - k1_t0) / 1e3))
     print("globaltimer span of CTA starts: %.1f us" % ((tr[:, 1].max() - g0) / 1e3))
     lt = tr[live]
     names = ["span-load", "window", "staging", "loop", "reduce"]
