@@ -244,12 +244,69 @@ def run_b200_arm(args):
     value = units * args.steps / (total_ms * 1e-3)
     e2e_value = units * args.steps / e2e_s
 
+    # ---- the dominant kernel alone (roofline): measurement mode of the C ABI puts CUDA events around the
+    #      row-setup kernel and the tile kernel of every call (L2 flushed between calls as above) ----
+    ctx.kernel_timing(True)
+    n_kt = max(5, min(args.steps, 20))
+    for _ in range(n_kt):
+        flush.zero_()
+        step_device()
+    rows_ms, tile_ms, pairs = ctx.kernel_timing(False)
+    torch.cuda.synchronize()
+
+    # ---- batched form of the same operator (extra, not the headline): 512 profiles, X-mode, n=20000 ----
+    batched = None
+    if rank == 0 and not args.no_batched:
+        from pyrayhf_b200 import synth
+        lat, lon = synth.grid_subset(512)
+        bden, bb, bpsi2 = synth.profiles_at(lat, lon, alt)
+        tb = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, bden, bb, bpsi2, alt)]
+        bout = torch.empty((512, freq.size), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            pyrayhf_b200.vertical_forward_operator_batched(*tb, MODE, N_POINTS, out=bout, errors='nan')
+        torch.cuda.synchronize()
+        bev = []
+        for _ in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            pyrayhf_b200.vertical_forward_operator_batched(*tb, MODE, N_POINTS, out=bout, errors='nan')
+            b.record(stream)
+            bev.append((a, b))
+        torch.cuda.synchronize()
+        b_ms = float(np.mean([a.elapsed_time(b) for a, b in bev]))
+        ctx.kernel_timing(True)
+        for _ in range(3):
+            pyrayhf_b200.vertical_forward_operator_batched(*tb, MODE, N_POINTS, out=bout, errors='nan')
+        _, b_tile_ms, b_pairs = ctx.kernel_timing(False)
+        bvh = bout.cpu().numpy()
+        b_live = int(np.isfinite(bvh).sum())
+        b_flops = sum(algorithmic_flops(bvh[q], bden[q])[0] for q in range(512))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pyrayhf_b200.vertical_forward_operator_batched(freq, bden, bb, bpsi2, alt, MODE, N_POINTS, errors='nan')
+        b_e2e = (time.perf_counter() - t0) / 3
+        batched = {"workload": "512 synthetic profiles (seeded subset of the 1-degree grid), X-mode, 174 freqs, n_points=20000",
+                   "value": 512 * freq.size / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms, "live_rows": b_live,
+                   "grid_points_per_s": b_live * N_POINTS / (b_ms * 1e-3),
+                   "tile_kernel_ms": b_tile_ms / max(b_pairs, 1),
+                   "tile_kernel_tflops": b_flops / (b_tile_ms / max(b_pairs, 1) * 1e-3) / 1e12,
+                   "e2e_value": 512 * freq.size / b_e2e, "e2e_ms_per_step": 1e3 * b_e2e,
+                   "e2e_h2d_bytes_per_step": int((freq.size + alt.size + 3 * 512 * alt.size) * 8),
+                   "e2e_d2h_bytes_per_step": int(512 * freq.size * 8 + 512 * 4)}
+
     if rank == 0:
         flops, live, at = algorithmic_flops(vh_dev, den)
-        kernel_ms = float(np.mean(step_ms))
+        kernel_ms = tile_ms / max(pairs, 1)               # the tile kernel alone, CUDA events on its stream
         peak_tf = ctx.measure_fp64_peak()
         achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
         hbm_bytes = 8 * freq.size + (3 * alt.size + alt.size + freq.size) * 8
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -259,9 +316,14 @@ def run_b200_arm(args):
                        "grid_points_per_s": live * N_POINTS * world / (total_ms / args.steps * 1e-3),
                        "l2": "flushed between timed steps (256 MiB write); every step timed with its own CUDA events"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": "prhf::vfo_tile_kernel<1,false>",
+                         "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "kernel": "prhf::vfo_tile_kernel<1,false>", "kernel_ms": kernel_ms,
+                         "rows_kernel_ms": rows_ms / max(pairs, 1),
+                         "step_frac": (flops / (total_ms / args.steps * 1e-3) / 1e12) / peak_tf,
                          "algorithmic_flops_per_launch": flops,
+                         "note": "achieved = W (77 flop per grid point of a reflecting row + 4 per profile level per row, "
+                                 "SURVEY 8d) / tile-kernel duration from CUDA events (prhf_kernel_timing); step_frac uses "
+                                 "the whole step (row-setup kernel + launch gaps included)",
                          "peak_source": "prhf_measure_fp64_peak: dependent-free DFMA kernel timed live on this GPU "
                                         "(MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_algorithmic_bytes_per_launch": hbm_bytes,
@@ -275,6 +337,9 @@ def run_b200_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        if batched:
+            batched["tile_kernel_frac_of_fp64_peak"] = batched["tile_kernel_tflops"] / peak_tf
+            line["batched"] = batched
         if world == 1 and not args.no_cpu_baseline:
             warnings.simplefilter("ignore")
             cb = cpu_numpy_port(steps=2, warmup=0, budget_s=30.0)
@@ -307,6 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -118,6 +118,11 @@ int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out);
  * out[4] / out[5] the seeds after one cubically convergent step. */
 int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err6);
 
+/* Measurement mode for the roofline: while enabled, prhf_vfo_f64 records CUDA events around the row-setup
+ * kernel and the tile kernel of every launch pair and synchronises on them (slower: no overlap between the
+ * two).  Each call returns the durations accumulated since the previous call, then clears them. */
+int prhf_kernel_timing(prhf_ctx* ctx, int enable, double* rows_kernel_ms, double* tile_kernel_ms, int* launch_pairs);
+
 /* Number of kernel launches issued through this ctx since creation (for bench accounting). */
 int64_t prhf_launch_count(const prhf_ctx* ctx);
 

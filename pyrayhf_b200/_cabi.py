@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "prhf_version", "prhf_error_string", "prhf_last_cuda_error", "prhf_ctx_create",
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
     "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
-    "prhf_selftest_math",
+    "prhf_selftest_math", "prhf_kernel_timing",
 )
 
 _vp = ctypes.c_void_p
@@ -86,6 +86,9 @@ def load():
         L.prhf_measure_fp64_peak.restype = _i
         L.prhf_selftest_math.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
         L.prhf_selftest_math.restype = _i
+        L.prhf_kernel_timing.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(_i)]
+        L.prhf_kernel_timing.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L
@@ -150,6 +153,13 @@ class Context:
         out = (ctypes.c_double * 6)()
         self.check(self._L.prhf_selftest_math(self._h, out))
         return list(out)
+
+    def kernel_timing(self, enable):
+        """(rows_kernel_ms, tile_kernel_ms, launch_pairs) accumulated since the last call; sets the mode."""
+        a, b, n = ctypes.c_double(), ctypes.c_double(), _i()
+        self.check(self._L.prhf_kernel_timing(self._h, int(bool(enable)), ctypes.byref(a), ctypes.byref(b),
+                                              ctypes.byref(n)))
+        return a.value, b.value, n.value
 
     def measure_fp64_peak(self):
         out = ctypes.c_double()

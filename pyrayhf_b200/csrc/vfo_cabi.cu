@@ -56,9 +56,15 @@ struct prhf_ctx {
   unsigned* live_count = nullptr;    // [2] one per call parity, followed by the fused kernel's barrier words [2]
   bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
+  bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
   int plan_parity = 0;
+  // optional per-kernel timing (bench roofline): events around K1 and K2 of every launch pair
+  bool kernel_timing = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  double k1_ms = 0.0, k2_ms = 0.0;
+  int timed_pairs = 0;
   // host entry graph cache; `epoch` changes whenever a device buffer baked into a graph is reallocated
   uint64_t epoch = 1;
   bool use_graphs = true;            // PRHF_NO_GRAPH=1 disables
@@ -257,6 +263,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_NO_GRAPH")) ctx->use_graphs = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_FUSED")) ctx->use_fused = (atoi(s) != 0);
   if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -272,6 +279,8 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
+  for (int k = 0; k < 3; ++k)
+    if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   for (auto& kv : ctx->graphs)
     for (int k = 0; k < 2; ++k)
       if (kv.second.exec[k]) cudaGraphExecDestroy(kv.second.exec[k]);
@@ -294,6 +303,20 @@ int prhf_max_n_alt(const prhf_ctx* ctx) {
 }
 
 int64_t prhf_launch_count(const prhf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int prhf_kernel_timing(prhf_ctx* ctx, int enable, double* rows_kernel_ms, double* tile_kernel_ms, int* launch_pairs) {
+  if (!ctx) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  if (rows_kernel_ms) *rows_kernel_ms = ctx->k1_ms;
+  if (tile_kernel_ms) *tile_kernel_ms = ctx->k2_ms;
+  if (launch_pairs) *launch_pairs = ctx->timed_pairs;
+  ctx->k1_ms = ctx->k2_ms = 0.0;
+  ctx->timed_pairs = 0;
+  if (enable && !ctx->ev[0])
+    for (int k = 0; k < 3; ++k) PRHF_CUDA(ctx, cudaEventCreate(&ctx->ev[k]));
+  ctx->kernel_timing = enable != 0;
+  return PRHF_OK;
+}
 
 #ifdef PRHF_TRACE
 // developer-only: allocate / read back the tile-kernel phase trace (not declared in the public header)
@@ -432,7 +455,7 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_cand = n_cand;
     for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
-    if (planned && ctx->use_fused) {
+    if (planned && ctx->use_fused && !ctx->kernel_timing) {
       // one cooperative launch: row setup, grid barrier, tiles
       const int rows_per_cta = prhf::kRowsPerCta * rows_per_warp;
       const int64_t n_items = np * ((n_freq + rows_per_cta - 1) / rows_per_cta);
@@ -444,9 +467,46 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
       cudaGetLastError();
       ctx->use_fused = false;                                 // e.g. cooperative launch unsupported: two launches
     }
-    PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
+    // direct mode with few grid points per row: row-per-warp kernel (profile staged once per CTA)
+    const bool rowwarp = !planned && n_seg == 1 && n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp;
+    int64_t rw_ctas = 0;
+    if (rowwarp) {
+      // whole profiles per CTA when there are enough profiles, else split the rows to get >= 4 waves of CTAs
+      int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(chunks8, ((int64_t)4 * slots + np - 1) / np));
+      P.rw_rows_per_cta = (int)((n_freq + chunks - 1) / chunks);
+      chunks = (n_freq + P.rw_rows_per_cta - 1) / P.rw_rows_per_cta;
+      rw_ctas = np * chunks;
+    } else {
+      P.rw_rows_per_cta = n_freq;
+    }
     // planned mode: enough CTAs for two waves of slots; they stride over however many tiles K1 planned
     const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots) : np * tiles_per_profile;
+    if (rowwarp && !ctx->kernel_timing) {
+      PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));
+      ctx->launches += 2;
+      continue;
+    }
+    if (ctx->kernel_timing) {
+      // measurement mode: events between the kernels (this serialises them: no PDL overlap)
+      P.use_pdl = 0;
+      PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
+      PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+      if (rowwarp) PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));
+      else PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
+      PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+      PRHF_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+      cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+      ctx->k1_ms += a;
+      ctx->k2_ms += b;
+      ctx->timed_pairs++;
+      ctx->launches += 2;
+      continue;
+    }
+    PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
     PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
     ctx->launches += 2;
   }

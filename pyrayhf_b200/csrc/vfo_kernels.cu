@@ -521,6 +521,9 @@ struct RowConst {
   double inv_dalt;  // (nt-1)/(alt[nt-1]-alt[0]): bracket guess for (near-)uniform altitude grids
   int nt;           // truncated length (= argmax(den))
   int jlo, jhi;     // node window staged for this tile (absolute indices)
+  int lane0;        // index of this thread inside the group that shares the row (CTA: tid, warp: lane)
+  int group;        // threads in that group (kTileThreads or 32)
+  double kx, ky;    // cp^2/f^2 and g_p/f, applied per point when the staged nodes are not pre-scaled
 };
 
 // Bracket of h inside the staged window: last j in [jlo, jhi] with alt[j] <= h (jlo - 1 if below).
@@ -625,7 +628,7 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
                                            int i0, int i1, int n_points, double mup0) {
   double acc0 = 0.0, acc1 = 0.0;
   const double2* m2 = reinterpret_cast<const double2*>(m);
-  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kTileThreads) {
+  for (int i = i0 + 2 * rc.lane0; i < i1; i += 2 * rc.group) {
     const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
     const double mn = __ldg(m + i + 2);
     const double h0 = __dadd_rn(__dmul_rn(mm.x, rc.span), rc.alt0);  // lib:413
@@ -671,16 +674,22 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
   return bracket_in<8>(h, &nodes[0].alt - (ptrdiff_t)jlo * 8, j + 1, jhi);
 }
 
-template <int MODE, int PATH>
-__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, int jlo, double* mu_out) {
-  const Node& nd = nodes[j - jlo];
+// ROWSCALE: the staged nodes are shared by several rows (row-per-warp kernel) and hold density / field
+// un-multiplied; the row's cp^2/f^2 and g_p/f are applied here (two more FP64 multiplies per point).
+template <int MODE, int PATH, bool ROWSCALE>
+__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out) {
+  const Node& nd = nodes[j - rc.jlo];
   const double t = h - nd.alt;
-  const double X = fma(nd.sx, t, nd.x);
+  double X = fma(nd.sx, t, nd.x);
+  if (ROWSCALE) X *= rc.kx;
   if (PATH == kPathFast0) {
     // node fields: y = Y sin(psi)/sqrt(2), sy its slope; srad = Y cos(psi), sn = its slope
-    return ah_hot<MODE>(X, fma(nd.sy, t, nd.y), fma(nd.sn, t, nd.srad), mu_out);
+    double yth = fma(nd.sy, t, nd.y), yl = fma(nd.sn, t, nd.srad);
+    if (ROWSCALE) { yth *= rc.ky; yl *= rc.ky; }
+    return ah_hot<MODE>(X, yth, yl, mu_out);
   }
-  const double Y = fma(nd.sy, t, nd.y);
+  double Y = fma(nd.sy, t, nd.y);
+  if (ROWSCALE) Y *= rc.ky;
   double sn, cs;
   if (PATH == kPathFastS) rotate_sincos_small(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
   else rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
@@ -698,13 +707,13 @@ __device__ __forceinline__ int bracket_uniform(double h, const Node* nodes, int 
   return max(j + up - down, jlo);
 }
 
-template <int MODE, int PATH, bool UNIFORM>
+template <int MODE, int PATH, bool UNIFORM, bool ROWSCALE>
 __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
                                                 int i0, int i1, int n_points) {
   double acc0 = 0.0, acc1 = 0.0;
   const double2* m2 = reinterpret_cast<const double2*>(m);
   const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
-  for (int i = i0 + 2 * (int)threadIdx.x; i < i1; i += 2 * kTileThreads) {
+  for (int i = i0 + 2 * rc.lane0; i < i1; i += 2 * rc.group) {
     const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
     const double mn = __ldg(m + i + 2);
     const double h0 = fma(mm.x, rc.span, rc.alt0);                   // lib:413
@@ -722,12 +731,103 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
       j1 = find_bracket_pos(h1, nodes, rc.jlo, rc.jhi, j0);
     }
     double mu0, mu1;
-    const double p0 = fast_point<MODE, PATH>(h0, j0, nodes, rc.jlo, &mu0);
-    const double p1 = fast_point<MODE, PATH>(h1, j1, nodes, rc.jlo, &mu1);
+    const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0);
+    const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1);
     acc0 = fma(keep_term(mu0, p0) ? p0 : 0.0, dh0, acc0);            // nansum (lib:288)
     acc1 = fma((keep_term(mu1, p1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
   }
   return acc0 + acc1;
+}
+
+// Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
+// of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
+// kernel (group = warp, ROWSCALE).
+template <int MODE, bool LITERAL, bool ROWSCALE>
+__device__ __forceinline__ double row_points(const Node* nodes, const RowConst& rc, int flags, int path, bool const_mup,
+                                             double den0, double b0, double psi0, const double* __restrict__ m,
+                                             int i0, int i1, int np) {
+  if (const_mup) {
+    // one evaluation at level 0 with the sign-safe / literal arithmetic, then sum(mu' * dh_i)
+    const double X = x_literal(den0, rc.f_hz);
+    double mup0;
+    if (path == kPathIso) {
+      mup0 = iso_mup(X, nullptr);
+    } else {
+      const double Y = y_literal(b0, rc.f_hz);
+      if (LITERAL) {
+        mup0 = ah_literal<MODE>(X, Y, psi0, nullptr);
+      } else {
+        double sn, cs;
+        sincos(__dmul_rn(psi0, kDeg2Rad), &sn, &cs);
+        mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
+      }
+    }
+    return tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
+  }
+  if (path < kPathGeneral) {
+    // uniform grids with more than one staged level take the branch-free bracket
+    const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
+    if (path == kPathFast0)
+      return uni ? tile_sum_fast<MODE, kPathFast0, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
+                 : tile_sum_fast<MODE, kPathFast0, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
+    if (path == kPathFastS)
+      return uni ? tile_sum_fast<MODE, kPathFastS, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
+                 : tile_sum_fast<MODE, kPathFastS, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
+    return uni ? tile_sum_fast<MODE, kPathFastL, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
+               : tile_sum_fast<MODE, kPathFastL, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
+  }
+  if (path == kPathIso) return tile_sum<MODE, kPathIso, false>(nodes, rc, m, i0, i1, np, 0.0);
+  if (LITERAL) return tile_sum<MODE, kPathLiteral, false>(nodes, rc, m, i0, i1, np, 0.0);
+  return tile_sum<MODE, kPathGeneral, false>(nodes, rc, m, i0, i1, np, 0.0);
+}
+
+// Stage profile levels [k0, k0 + n) into shared memory.  Fast paths: slopes through one fast reciprocal, density
+// and field multiplied by (kx, ky) (the row's cp^2/f^2 and g_p/f, or 1 when the nodes are shared between rows);
+// other paths: raw values and numpy's slopes.
+__device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, int path, const ProfileRecord& rec,
+                                            const double* g_alt, const double* g_den, const double* g_b,
+                                            const double* g_psi, double kx, double ky, int tid0, int nthr) {
+  const bool fast = path < kPathGeneral;
+  for (int q = tid0; q < n; q += nthr) {
+    const int k = k0 + q;
+    const bool inner = k + 1 < nt;
+    const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
+    const double a1 = inner ? g_alt[k + 1] : a0, d1 = inner ? g_den[k + 1] : d0;
+    const double b1 = inner ? g_b[k + 1] : b0, p1 = inner ? g_psi[k + 1] : p0;
+    Node nd;
+    nd.alt = a0;
+    if (fast) {
+      // slopes through one fast reciprocal (<= 2 ulp from numpy's quotient; the literal paths divide)
+      const double inv_dx = inner ? rcp_fast(a1 - a0) : 0.0;
+      nd.x = d0 * kx;
+      nd.sx = ((d1 - d0) * kx) * inv_dx;
+      nd.y = b0 * ky;
+      nd.sy = ((b1 - b0) * ky) * inv_dx;
+      nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
+      if (path == kPathFast0) {
+        // constant field angle: interpolate YTh = Y sin(psi)/sqrt(2) and YL = Y cos(psi) directly
+        const double sh = rec.sn0 * 0.70710678118654752, cc = rec.cs0;
+        const double y0 = nd.y, sy0 = nd.sy;
+        nd.y = y0 * sh;
+        nd.sy = sy0 * sh;
+        nd.srad = y0 * cc;
+        nd.sn = sy0 * cc;
+        nd.cs = 0.0;
+      } else {
+        sincos(p0 * kDeg2Rad, &nd.sn, &nd.cs);
+      }
+    } else {
+      double sd = 0.0, sb = 0.0, sp = 0.0;
+      if (inner) {                                        // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
+        const double dx = __dsub_rn(a1, a0);
+        sd = __ddiv_rn(__dsub_rn(d1, d0), dx);
+        sb = __ddiv_rn(__dsub_rn(b1, b0), dx);
+        sp = __ddiv_rn(__dsub_rn(p1, p0), dx);
+      }
+      nd.x = d0; nd.sx = sd; nd.y = b0; nd.sy = sb; nd.srad = sp; nd.sn = p0; nd.cs = 0.0;
+    }
+    nodes[q] = nd;
+  }
 }
 
 // ProfileRecord through L2 (ld.cg): in the fused kernel it was written by another CTA of the same launch.
@@ -772,8 +872,6 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   else if (rec.flags & kFlagPsiConst) path = kPathFast0;
   else if (rec.flags & kFlagPsiSmall) path = kPathFastS;
   else path = kPathFastL;
-  const bool fast = path < kPathGeneral;
-
   const int A = p.n_alt;
   const double* g_den = p.den + prof * A;
   const double* g_b = p.bmag + prof * A;
@@ -820,89 +918,17 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
-  for (int q = tid; q < n_stage; q += kTileThreads) {
-    const int k = rc.jlo + q;
-    const bool inner = k + 1 < nt;
-    const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
-    const double a1 = inner ? g_alt[k + 1] : a0, d1 = inner ? g_den[k + 1] : d0;
-    const double b1 = inner ? g_b[k + 1] : b0, p1 = inner ? g_psi[k + 1] : p0;
-    Node nd;
-    nd.alt = a0;
-    if (fast) {
-      // slopes through one fast reciprocal (<= 2 ulp from numpy's quotient; the literal paths divide)
-      const double inv_dx = inner ? rcp_fast(a1 - a0) : 0.0;
-      nd.x = d0 * kx;
-      nd.sx = ((d1 - d0) * kx) * inv_dx;
-      nd.y = b0 * ky;
-      nd.sy = ((b1 - b0) * ky) * inv_dx;
-      nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
-      if (path == kPathFast0) {
-        // constant field angle: interpolate YTh = Y sin(psi)/sqrt(2) and YL = Y cos(psi) directly
-        const double sh = rec.sn0 * 0.70710678118654752, cc = rec.cs0;
-        const double y0 = nd.y, sy0 = nd.sy;
-        nd.y = y0 * sh;
-        nd.sy = sy0 * sh;
-        nd.srad = y0 * cc;
-        nd.sn = sy0 * cc;
-        nd.cs = 0.0;
-      } else {
-        sincos(p0 * kDeg2Rad, &nd.sn, &nd.cs);
-      }
-    } else {
-      double sd = 0.0, sb = 0.0, sp = 0.0;
-      if (inner) {                                        // numpy: slopes[k] = (fp[k+1]-fp[k])/(xp[k+1]-xp[k])
-        const double dx = __dsub_rn(a1, a0);
-        sd = __ddiv_rn(__dsub_rn(d1, d0), dx);
-        sb = __ddiv_rn(__dsub_rn(b1, b0), dx);
-        sp = __ddiv_rn(__dsub_rn(p1, p0), dx);
-      }
-      nd.x = d0; nd.sx = sd; nd.y = b0; nd.sy = sb; nd.srad = sp; nd.sn = p0; nd.cs = 0.0;
-    }
-    nodes[q] = nd;
-  }
+  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads);
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
   // ---- grid points of the tile ----
-  double acc;
-  const double* m = p.mult;
-  const int np = p.n_points;
-  if (const_mup) {
-    // one evaluation at level 0 with the sign-safe / literal arithmetic, then sum(mu' * dh_i)
-    const double X = x_literal(g_den[0], rc.f_hz);
-    double mup0;
-    if (path == kPathIso) {
-      mup0 = iso_mup(X, nullptr);
-    } else {
-      const double Y = y_literal(g_b[0], rc.f_hz);
-      if (LITERAL) {
-        mup0 = ah_literal<MODE>(X, Y, g_psi[0], nullptr);
-      } else {
-        double sn, cs;
-        sincos(__dmul_rn(g_psi[0], kDeg2Rad), &sn, &cs);
-        mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
-      }
-    }
-    acc = tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
-  } else if (fast) {
-    // uniform grids with more than one staged level take the branch-free bracket
-    const bool uni = (rec.flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
-    if (path == kPathFast0)
-      acc = uni ? tile_sum_fast<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np)
-                : tile_sum_fast<MODE, kPathFast0, false>(nodes, rc, m, i0, i1, np);
-    else if (path == kPathFastS)
-      acc = uni ? tile_sum_fast<MODE, kPathFastS, true>(nodes, rc, m, i0, i1, np)
-                : tile_sum_fast<MODE, kPathFastS, false>(nodes, rc, m, i0, i1, np);
-    else
-      acc = uni ? tile_sum_fast<MODE, kPathFastL, true>(nodes, rc, m, i0, i1, np)
-                : tile_sum_fast<MODE, kPathFastL, false>(nodes, rc, m, i0, i1, np);
-  } else if (path == kPathIso) {
-    acc = tile_sum<MODE, kPathIso, false>(nodes, rc, m, i0, i1, np, 0.0);
-  } else if (LITERAL) {
-    acc = tile_sum<MODE, kPathLiteral, false>(nodes, rc, m, i0, i1, np, 0.0);
-  } else {
-    acc = tile_sum<MODE, kPathGeneral, false>(nodes, rc, m, i0, i1, np, 0.0);
-  }
+  rc.lane0 = tid;
+  rc.group = kTileThreads;
+  rc.kx = kx;
+  rc.ky = ky;
+  const double acc = row_points<MODE, LITERAL, false>(nodes, rc, rec.flags, path, const_mup, g_den[0], g_b[0], g_psi[0],
+                                                      p.mult, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
   PRHF_TRACE_MARK(6);
@@ -972,6 +998,75 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
     return;
   }
   planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
+}
+
+// Row-per-warp form for small n_points (direct mode): one CTA stages the profile's levels ONCE (un-scaled)
+// and its warps each take whole rows, so neither the staging (~100 FP64 instructions per level) nor a
+// block-wide barrier is paid per 200-point row.  Rows that do not reflect are skipped on their row_span.
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the row-setup grid has completed (no-op without PDL)
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunks = (p.n_freq + p.rw_rows_per_cta - 1) / p.rw_rows_per_cta;
+  const int64_t lprof = blockIdx.x / chunks;
+  const int r_begin = (int)(blockIdx.x % chunks) * p.rw_rows_per_cta;
+  const int r_end = min(p.n_freq, r_begin + p.rw_rows_per_cta);
+  const int64_t prof = p.profile_offset + lprof;
+  const ProfileRecord rec = load_profile_record(p.prof_rec + lprof);
+  if (rec.flags & kFlagFailed) return;                    // K1 wrote the NaN rows and the status
+  // anything to do in this chunk?
+  bool live = false;
+  for (int r = r_begin + tid; r < r_end; r += kTileThreads) {
+    const double sp = p.row_span[lprof * p.n_freq + r];
+    live |= (sp == sp);
+  }
+  if (!__syncthreads_or(live)) return;
+
+  const int nt = rec.nt;
+  int path;
+  if (rec.flags & kFlagIso) path = kPathIso;
+  else if (LITERAL) path = kPathLiteral;
+  else if (rec.flags & kFlagGeneral) path = kPathGeneral;
+  else if (rec.flags & kFlagPsiConst) path = kPathFast0;
+  else if (rec.flags & kFlagPsiSmall) path = kPathFastS;
+  else path = kPathFastL;
+
+  const int A = p.n_alt;
+  const double* g_den = p.den + prof * A;
+  const double* g_b = p.bmag + prof * A;
+  const double* g_psi = p.bpsi + prof * A;
+  const double* g_alt = p.alt + prof * p.alt_stride;
+  Node* nodes = reinterpret_cast<Node*>(smem_raw);
+  stage_nodes(nodes, 0, nt, nt, path, rec, g_alt, g_den, g_b, g_psi, 1.0, 1.0, tid, kTileThreads);
+  __syncthreads();
+  const double den0 = g_den[0], b0 = g_b[0], psi0 = g_psi[0];
+
+  for (int r = r_begin + wid; r < r_end; r += kTileThreads / 32) {
+    const int64_t lrow = lprof * p.n_freq + r;
+    const double span = p.row_span[lrow];
+    if (!(span == span)) continue;
+    RowConst rc;
+    rc.f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);
+    rc.alt0 = rec.alt0;
+    rc.span = span;
+    rc.inv_dalt = rec.inv_dalt;
+    rc.nt = nt;
+    rc.kx = (kCp * kCp) / (rc.f_hz * rc.f_hz);
+    rc.ky = kGp / rc.f_hz;
+    rc.lane0 = lane;
+    rc.group = 32;
+    const bool const_mup = !(span > 0.0) || nt == 1;       // h_c <= alt0: every point clamps to level 0
+    rc.jlo = 0;
+    rc.jhi = const_mup ? 0 : nt - 1;
+    double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, p.mult, 0,
+                                                 p.n_points, p.n_points);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (acc == 0.0) acc = CUDART_NAN;                   // lib:290
+      p.vh[prof * p.n_freq + r] = acc + rec.alt_min;      // lib:292
+    }
+  }
 }
 
 // Fused form of the planned mode (small batches), launched cooperatively with one wave of CTAs: the row
@@ -1111,6 +1206,35 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   vfo_rows_kernel<<<(unsigned)(n_profiles * chunks), kThreads, smem, stream>>>(p, mode);
   return cudaGetLastError();
+}
+
+template <int MODE, bool LITERAL>
+static cudaError_t launch_rowwarp_t(const VfoParams& p, int64_t n_ctas, cudaStream_t stream) {
+  const size_t smem = vfo_tile_smem_bytes(p.n_alt);
+  auto kern = vfo_rowwarp_kernel<MODE, LITERAL>;
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 9 + MODE * 2 + (LITERAL ? 1 : 0), smem);
+  if (e != cudaSuccess) return e;
+  if (!p.use_pdl) {
+    kern<<<(unsigned)n_ctas, kTileThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(kTileThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream) {
+  if (mode == 0)
+    return literal ? launch_rowwarp_t<0, true>(p, n_ctas, stream) : launch_rowwarp_t<0, false>(p, n_ctas, stream);
+  return literal ? launch_rowwarp_t<1, true>(p, n_ctas, stream) : launch_rowwarp_t<1, false>(p, n_ctas, stream);
 }
 
 int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm) {

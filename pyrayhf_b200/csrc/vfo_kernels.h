@@ -17,6 +17,7 @@ constexpr int kMaxWarps = 8;
 constexpr int kTileThreads = PRHF_TILE_THREADS;   // K2 block size (multiple of 64, <= 256)
 constexpr int kTileMinBlocks = PRHF_TILE_MINB;    // K2 resident CTAs per SM the register budget targets
 constexpr int kRowsPerCta = kThreads / 32;   // K1: one warp per sounding frequency
+constexpr int kRowWarpMaxPoints = 4096;      // direct-mode calls with n_points up to this use the row-per-warp kernel
 constexpr int kMultPad = 4;                  // extra multiplier-table entries (value 1) past n_points
 
 constexpr int kFlagIso = 1;       // unmagnetised branch (lib:201)
@@ -63,6 +64,7 @@ struct VfoParams {
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
   int rows_per_warp;       // K1: sounding frequencies handled by one warp (CTA = 8 warps)
+  int rw_rows_per_cta;     // row-per-warp kernel: rows of one profile handled by one CTA
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null
   ProfileRecord* prof_rec; // [profiles_in_launch]
@@ -89,6 +91,7 @@ size_t vfo_smem_bytes(int n_alt);
 int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
+cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
 cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
