@@ -57,6 +57,7 @@ struct prhf_ctx {
   bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
+  bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
   int plan_parity = 0;
@@ -264,6 +265,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_FUSED")) ctx->use_fused = (atoi(s) != 0);
   if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_NO_K1_LANES")) ctx->use_k1_lanes = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -430,6 +432,7 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.seg_len = seg_len;
     P.n_seg = n_seg;
     P.rows_per_warp = rows_per_warp;
+    P.k1_lane_mode = (!planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count) ? 1 : 0;
     P.vh = vh_out;
     P.status = status;
     P.prof_rec = ctx->prof_rec;

@@ -244,7 +244,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   double* s_crit = s_psi + A;    // [kRowsPerCta][A]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
+  const int rows_per_cta = p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp;
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   const int64_t lprof = item / chunks;                  // profile index inside this launch
   const int g = (int)(item % chunks);
@@ -347,6 +347,114 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     if (p.status) p.status[prof] = status;
   }
   PRHF_TRACE_K1(3);
+  // ---- lane-per-row scan (large batches): thread t takes sounding frequency g * 256 + t ----
+  // Same decisions as the warp-per-row scan below, organised so that the loop over the profile levels is
+  // uniform across the warp (shared-memory broadcasts, no divergence) and the literal evaluations happen
+  // in lock-step: pass A screens every level and remembers, per row, the first level that may reach 1
+  // (cand) and the largest screen value below it (kmax) with its runner-up; pass B evaluates those two
+  // levels literally.  Rows where the screen cannot separate the candidates (values within kScreenTol of a
+  // decision, or a literal candidate that turns out <= 1) fall back to a sequential literal scan.
+  if (p.k1_lane_mode) {
+    const int r = g * kThreads + tid;
+    if (r >= p.n_freq) return;
+    const int64_t out_idx = prof * p.n_freq + r;
+    const int64_t lrow = lprof * p.n_freq + r;
+    if (status != 0) {
+      p.vh[out_idx] = CUDART_NAN;
+      p.row_span[lrow] = CUDART_NAN;
+      return;
+    }
+    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+    const double kx = (kCp * kCp) / __dmul_rn(f_hz, f_hz);
+    const double ky = (mode == 1) ? kGp / f_hz : 0.0;
+    bool slow = any_general || !(isfinite(kx) && isfinite(ky) && kx > 0.0);
+    int jstar = 0x7fffffff;
+    bool any_eq1 = false, has_nan = false;
+    double v_jstar = 0.0, M = -CUDART_INF;
+    if (!slow) {
+      int cand = -1, kmax = -1;
+      double amax = -CUDART_INF, a2 = -CUDART_INF, smax = 0.0;
+      for (int k = 0; k < nt; ++k) {
+        const double xk = s_den[k] * kx, yk = s_b[k] * ky;
+        const double a = xk + yk, sabs = fabs(xk) + fabs(yk);
+        if (cand < 0) {
+          if (a >= 1.0 - kScreenTol * sabs) {
+            cand = k;
+          } else {
+            if (a > amax) { a2 = amax; amax = a; kmax = k; }
+            else if (a > a2) a2 = a;
+            smax = fmax(smax, sabs);
+          }
+        }
+        if ((k & 15) == 15 && __all_sync(__activemask(), cand >= 0)) break;
+      }
+      if (cand >= 0) {
+        double v = x_literal(s_den[cand], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[cand], f_hz));
+        if (v > 1.0) {
+          jstar = cand;
+          v_jstar = v;
+          if (cand > 0) {
+            if (a2 < amax - 2.0 * kScreenTol * smax) {    // one level clearly holds the running max
+              M = x_literal(s_den[kmax], f_hz);
+              if (mode == 1) M = __dadd_rn(M, y_literal(s_b[kmax], f_hz));
+            } else {
+              slow = true;
+            }
+          }
+        } else {
+          slow = true;                                    // the literal value did not cross: scan on literally
+        }
+      }
+    }
+    if (slow) {                                           // sequential literal scan (lib:380-399 as written)
+      jstar = 0x7fffffff;
+      M = -CUDART_INF;
+      double run = 0.0;
+      for (int k = 0; k < nt; ++k) {
+        double v = x_literal(s_den[k], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+        has_nan |= isnan(v);
+        if (jstar == 0x7fffffff) {
+          if (v > 1.0) { jstar = k; v_jstar = v; M = run; }
+          else { run = (k == 0) ? v : fmax(run, v); any_eq1 |= (v == 1.0); }
+        }
+      }
+    }
+    const bool dead = has_nan || (jstar == 0x7fffffff && !any_eq1);
+    if (dead) {                                           // valid == False (lib:399) -> NaN (lib:407)
+      double res = CUDART_NAN;
+      if (nt == 1) {                                      // numpy's single-node np.interp quirk, see below
+        const double X = x_literal(s_den[0], f_hz);
+        double mup;
+        if (iso) mup = iso_mup(X, nullptr);
+        else if (mode == 0) mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
+        else mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
+        const double term = mup * kBackoff;
+        if (term == term && term != 0.0) res = term + alt_min;
+      }
+      p.vh[out_idx] = res;
+      p.row_span[lrow] = CUDART_NAN;
+      return;
+    }
+    double hcrit;
+    if (jstar == 0 || nt == 1) {
+      hcrit = s_alt[0];
+    } else if (jstar == 0x7fffffff) {
+      hcrit = s_alt[nt - 1];
+    } else {
+      const int j = jstar - 1;
+      if (M == 1.0) {
+        hcrit = s_alt[j];
+      } else {
+        const double slope = __ddiv_rn(__dsub_rn(s_alt[j + 1], s_alt[j]), __dsub_rn(v_jstar, M));
+        hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
+      }
+    }
+    p.row_span[lrow] = __dsub_rn(__dsub_rn(hcrit, kBackoff), s_alt[0]);   // lib:407, lib:413
+    return;
+  }
+
   // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
   double* crit = s_crit + (size_t)wid * A;
   for (int rr = 0; rr < p.rows_per_warp; ++rr) {
@@ -1202,7 +1310,7 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
   const size_t smem = vfo_rows_smem_bytes(p.n_alt);
   cudaError_t e = grant_dynamic_smem((const void*)vfo_rows_kernel, 0, smem);
   if (e != cudaSuccess) return e;
-  const int rows_per_cta = kRowsPerCta * p.rows_per_warp;
+  const int rows_per_cta = p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp;
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   vfo_rows_kernel<<<(unsigned)(n_profiles * chunks), kThreads, smem, stream>>>(p, mode);
   return cudaGetLastError();

@@ -64,6 +64,7 @@ struct VfoParams {
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
   int rows_per_warp;       // K1: sounding frequencies handled by one warp (CTA = 8 warps)
+  int k1_lane_mode;        // K1: one thread per sounding frequency (large batches) instead of one warp
   int rw_rows_per_cta;     // row-per-warp kernel: rows of one profile handled by one CTA
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null
