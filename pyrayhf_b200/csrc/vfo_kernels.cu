@@ -233,6 +233,105 @@ __device__ __forceinline__ int bracket_in(double x, const double* xp, int lo, in
 // ==========================================================================================
 // K1: per-row setup
 // ==========================================================================================
+// Result of the critical-curve scan of one row.
+struct RowScan {
+  int jstar;        // first level whose literal value exceeds 1 (0x7fffffff: none)
+  double v_jstar;   // its literal value
+  double M;         // literal running max just below it
+  bool any_eq1;     // some literal value equals 1 exactly (matters only when jstar is none)
+  bool has_nan;
+};
+
+// Warp-per-row scan:
+// screen == true: iterate over screen candidates until a literal value exceeds 1, then evaluate literally
+// every level whose screen value is within tolerance of the running max; screen == false (non-finite
+// inputs): literal values at every level.
+__device__ __forceinline__ RowScan row_scan_general(bool screen, int mode, int nt, int lane, double f_hz, double kx,
+                                                 double ky, const double* s_den, const double* s_b, double* crit) {
+  int jstar = 0x7fffffff;
+  bool any_eq1 = false, has_nan = false;
+  double v_jstar = 0.0, M = -CUDART_INF;
+  if (screen) {
+      for (int k = lane; k < nt; k += 32) crit[k] = fma(s_b[k], ky, s_den[k] * kx);
+      __syncwarp();
+      int start = 0;
+      for (;;) {
+        int cand = 0x7fffffff;
+        for (int k = lane; k < nt; k += 32) {
+          if (k < start) continue;
+          const double tol = kScreenTol * (fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
+          if (crit[k] >= 1.0 - tol) { cand = k; break; }
+        }
+        cand = warp_min_i(cand);
+        if (cand == 0x7fffffff) break;
+        double v = x_literal(s_den[cand], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[cand], f_hz));
+        if (v > 1.0) { jstar = cand; v_jstar = v; break; }
+        if (v == 1.0) any_eq1 = true;
+        start = cand + 1;
+      }
+      if (jstar != 0x7fffffff && jstar > 0) {
+        double amax = -CUDART_INF, smax = 0.0;
+        for (int k = lane; k < jstar; k += 32) {
+          amax = fmax(amax, crit[k]);
+          smax = fmax(smax, fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
+        }
+        amax = warp_max(amax);
+        const double thr = amax - 2.0 * kScreenTol * warp_max(smax);
+        for (int k = lane; k < jstar; k += 32) {
+          if (crit[k] >= thr) {
+            double v = x_literal(s_den[k], f_hz);
+            if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+            M = fmax(M, v);
+          }
+        }
+        M = warp_max(M);                                   // cummax[jstar-1], literal
+      }
+  } else {
+      int first_gt = 0x7fffffff;
+      bool any_ge = false;
+      for (int k = lane; k < nt; k += 32) {
+        double v = x_literal(s_den[k], f_hz);
+        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
+        crit[k] = v;
+        has_nan |= isnan(v);
+        any_ge |= (v >= 1.0);
+        if (v > 1.0) first_gt = min(first_gt, k);
+      }
+      jstar = warp_min_i(first_gt);
+      has_nan = __any_sync(0xffffffffu, has_nan);
+      any_eq1 = __any_sync(0xffffffffu, any_ge);           // with jstar == none this means max == 1.0
+      __syncwarp();
+      if (jstar != 0x7fffffff && jstar > 0) {
+        double pm = -CUDART_INF;
+        for (int k = lane; k < jstar; k += 32) pm = fmax(pm, crit[k]);
+        M = warp_max(pm);
+        v_jstar = crit[jstar];
+      }
+    }
+  RowScan out;
+  out.jstar = jstar;
+  out.v_jstar = v_jstar;
+  out.M = M;
+  out.any_eq1 = any_eq1;
+  out.has_nan = has_nan;
+  return out;
+}
+
+// numpy's single-node np.interp has no NaN test: interp(NaN, [x0], [f0]) == f0.  A dead row of a one-level
+// profile therefore still sees finite den/bmag/bpsi, every dh is NaN except the final 1e-6 (lib:416), and
+// the reference returns alt_min + mu'(level 0) * 1e-6.
+__device__ __noinline__ double dead_row_single_level(int mode, bool iso, double den0, double b0, double psi0,
+                                                     double f_hz, double alt_min) {
+  const double X = x_literal(den0, f_hz);
+  double mup;
+  if (iso) mup = iso_mup(X, nullptr);
+  else if (mode == 0) mup = ah_literal<0>(X, y_literal(b0, f_hz), psi0, nullptr);
+  else mup = ah_literal<1>(X, y_literal(b0, f_hz), psi0, nullptr);
+  const double term = mup * kBackoff;
+  return (term == term && term != 0.0) ? term + alt_min : CUDART_NAN;
+}
+
 // `item` = (profile index inside the launch) * chunks + chunk of sounding frequencies.
 __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, const int64_t item, double* smem,
                                           BlockScratch& sc) {
@@ -423,16 +522,8 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     }
     const bool dead = has_nan || (jstar == 0x7fffffff && !any_eq1);
     if (dead) {                                           // valid == False (lib:399) -> NaN (lib:407)
-      double res = CUDART_NAN;
-      if (nt == 1) {                                      // numpy's single-node np.interp quirk, see below
-        const double X = x_literal(s_den[0], f_hz);
-        double mup;
-        if (iso) mup = iso_mup(X, nullptr);
-        else if (mode == 0) mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
-        else mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
-        const double term = mup * kBackoff;
-        if (term == term && term != 0.0) res = term + alt_min;
-      }
+      const double res = (nt == 1) ? dead_row_single_level(mode, iso, s_den[0], s_b[0], s_psi[0], f_hz, alt_min)
+                                   : CUDART_NAN;
       p.vh[out_idx] = res;
       p.row_span[lrow] = CUDART_NAN;
       return;
@@ -481,85 +572,19 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     int jstar = 0x7fffffff;
     bool any_eq1 = false, has_nan = false;
     double v_jstar = 0.0, M = -CUDART_INF;
-    if (screen) {
-      for (int k = lane; k < nt; k += 32) crit[k] = fma(s_b[k], ky, s_den[k] * kx);
-      __syncwarp();
-      int start = 0;
-      for (;;) {
-        int cand = 0x7fffffff;
-        for (int k = lane; k < nt; k += 32) {
-          if (k < start) continue;
-          const double tol = kScreenTol * (fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
-          if (crit[k] >= 1.0 - tol) { cand = k; break; }
-        }
-        cand = warp_min_i(cand);
-        if (cand == 0x7fffffff) break;
-        double v = x_literal(s_den[cand], f_hz);
-        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[cand], f_hz));
-        if (v > 1.0) { jstar = cand; v_jstar = v; break; }
-        if (v == 1.0) any_eq1 = true;
-        start = cand + 1;
-      }
-      if (jstar != 0x7fffffff && jstar > 0) {
-        double amax = -CUDART_INF, smax = 0.0;
-        for (int k = lane; k < jstar; k += 32) {
-          amax = fmax(amax, crit[k]);
-          smax = fmax(smax, fabs(s_den[k] * kx) + fabs(s_b[k] * ky));
-        }
-        amax = warp_max(amax);
-        const double thr = amax - 2.0 * kScreenTol * warp_max(smax);
-        for (int k = lane; k < jstar; k += 32) {
-          if (crit[k] >= thr) {
-            double v = x_literal(s_den[k], f_hz);
-            if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
-            M = fmax(M, v);
-          }
-        }
-        M = warp_max(M);                                   // cummax[jstar-1], literal
-      }
-    } else {
-      int first_gt = 0x7fffffff;
-      bool any_ge = false;
-      for (int k = lane; k < nt; k += 32) {
-        double v = x_literal(s_den[k], f_hz);
-        if (mode == 1) v = __dadd_rn(v, y_literal(s_b[k], f_hz));
-        crit[k] = v;
-        has_nan |= isnan(v);
-        any_ge |= (v >= 1.0);
-        if (v > 1.0) first_gt = min(first_gt, k);
-      }
-      jstar = warp_min_i(first_gt);
-      has_nan = __any_sync(0xffffffffu, has_nan);
-      any_eq1 = __any_sync(0xffffffffu, any_ge);           // with jstar == none this means max == 1.0
-      __syncwarp();
-      if (jstar != 0x7fffffff && jstar > 0) {
-        double pm = -CUDART_INF;
-        for (int k = lane; k < jstar; k += 32) pm = fmax(pm, crit[k]);
-        M = warp_max(pm);
-        v_jstar = crit[jstar];
-      }
+    {
+      const RowScan rs = row_scan_general(screen, mode, nt, lane, f_hz, kx, ky, s_den, s_b, crit);
+      jstar = rs.jstar;
+      v_jstar = rs.v_jstar;
+      M = rs.M;
+      any_eq1 = rs.any_eq1;
+      has_nan = rs.has_nan;
     }
     const bool dead = has_nan || (jstar == 0x7fffffff && !any_eq1);
     if (dead) {                                             // valid == False (lib:399) -> NaN (lib:407)
       if (lane == 0) {
-        double res = CUDART_NAN;
-        if (nt == 1) {
-          // numpy's single-node np.interp has no NaN test: interp(NaN, [x0], [f0]) == f0.  A dead row of a
-          // one-node profile therefore still sees finite den/bmag/bpsi, every dh is NaN except the final
-          // 1e-6 (lib:416), and the reference returns alt_min + mu'(node 0) * 1e-6.
-          const double X = x_literal(s_den[0], f_hz);
-          double mup;
-          if (iso) {
-            mup = iso_mup(X, nullptr);
-          } else if (mode == 0) {
-            mup = ah_literal<0>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
-          } else {
-            mup = ah_literal<1>(X, y_literal(s_b[0], f_hz), s_psi[0], nullptr);
-          }
-          const double term = mup * kBackoff;
-          if (term == term && term != 0.0) res = term + alt_min;
-        }
-        p.vh[out_idx] = res;
+        p.vh[out_idx] = (nt == 1) ? dead_row_single_level(mode, iso, s_den[0], s_b[0], s_psi[0], f_hz, alt_min)
+                                  : CUDART_NAN;
         p.row_span[lrow] = CUDART_NAN;
       }
       __syncwarp();
@@ -850,28 +875,42 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
 // Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
 // of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
 // kernel (group = warp, ROWSCALE).
+// Out-of-line copies of the rarely used evaluation paths (non-finite inputs, literal flag, unmagnetised
+// profiles, rows clamped to level 0): keeps the hot fast-path loop compact in the instruction cache.
+template <int MODE, int PATH>
+__device__ __noinline__ double tile_sum_cold(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                             int i0, int i1, int np) {
+  return tile_sum<MODE, PATH, false>(nodes, rc, m, i0, i1, np, 0.0);
+}
+template <int MODE, bool LITERAL>
+__device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& rc, int path, double den0, double b0,
+                                             double psi0, const double* __restrict__ m, int i0, int i1, int np) {
+  // one evaluation at level 0 with the sign-safe / literal arithmetic, then sum(mu' * dh_i)
+  const double X = x_literal(den0, rc.f_hz);
+  double mup0;
+  if (path == kPathIso) {
+    mup0 = iso_mup(X, nullptr);
+  } else {
+    const double Y = y_literal(b0, rc.f_hz);
+    if (LITERAL) {
+      mup0 = ah_literal<MODE>(X, Y, psi0, nullptr);
+    } else {
+      double sn, cs;
+      sincos(__dmul_rn(psi0, kDeg2Rad), &sn, &cs);
+      mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
+    }
+  }
+  return tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
+}
+
+// Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
+// of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
+// kernel (group = warp, ROWSCALE).
 template <int MODE, bool LITERAL, bool ROWSCALE>
 __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& rc, int flags, int path, bool const_mup,
                                              double den0, double b0, double psi0, const double* __restrict__ m,
                                              int i0, int i1, int np) {
-  if (const_mup) {
-    // one evaluation at level 0 with the sign-safe / literal arithmetic, then sum(mu' * dh_i)
-    const double X = x_literal(den0, rc.f_hz);
-    double mup0;
-    if (path == kPathIso) {
-      mup0 = iso_mup(X, nullptr);
-    } else {
-      const double Y = y_literal(b0, rc.f_hz);
-      if (LITERAL) {
-        mup0 = ah_literal<MODE>(X, Y, psi0, nullptr);
-      } else {
-        double sn, cs;
-        sincos(__dmul_rn(psi0, kDeg2Rad), &sn, &cs);
-        mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
-      }
-    }
-    return tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
-  }
+  if (const_mup) return const_mup_sum<MODE, LITERAL>(nodes, rc, path, den0, b0, psi0, m, i0, i1, np);
   if (path < kPathGeneral) {
     // uniform grids with more than one staged level take the branch-free bracket
     const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
@@ -884,9 +923,9 @@ __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& 
     return uni ? tile_sum_fast<MODE, kPathFastL, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
                : tile_sum_fast<MODE, kPathFastL, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
   }
-  if (path == kPathIso) return tile_sum<MODE, kPathIso, false>(nodes, rc, m, i0, i1, np, 0.0);
-  if (LITERAL) return tile_sum<MODE, kPathLiteral, false>(nodes, rc, m, i0, i1, np, 0.0);
-  return tile_sum<MODE, kPathGeneral, false>(nodes, rc, m, i0, i1, np, 0.0);
+  if (path == kPathIso) return tile_sum_cold<MODE, kPathIso>(nodes, rc, m, i0, i1, np);
+  if (LITERAL) return tile_sum_cold<MODE, kPathLiteral>(nodes, rc, m, i0, i1, np);
+  return tile_sum_cold<MODE, kPathGeneral>(nodes, rc, m, i0, i1, np);
 }
 
 // Stage profile levels [k0, k0 + n) into shared memory.  Fast paths: slopes through one fast reciprocal, density

@@ -334,3 +334,27 @@ def test_row_setup_lane_mode_matches_warp_mode(vfo, golden, mode, monkeypatch):
     assert_parity(a[:, :sy["freq"].size], sy["ref_%s_200" % mode], sy["truth_%s_200" % mode], mode, "lane-mode K1")
     ref = vfo_oracle.vertical_forward_operator(freq, den[0], bmag[0], bpsi[0], sy["alt"], mode, 200)
     assert np.array_equal(np.isnan(a[0]), np.isnan(ref))
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_config5_frequency_sweep_full_size(vfo, golden, mode):
+    """BASELINE configs[4]: 1740 frequencies (0.01 MHz step) at n_points = 50000 on the tutorial Day profile.
+    The numpy oracle would need ~14 GB of temporaries here, so the checker is the scalar C oracle:
+    its literal variant is within 1e-11 of the reference in X-mode (test_oracle_golden) and its long-double
+    variant is the O-mode truth.  Rows within 0.05 MHz of the truncated-peak cutoff are reported separately."""
+    fx = golden.fixtures
+    den, bmag, bpsi, alt = (fx["Day_" + k] for k in ("den", "bmag", "bpsi", "alt"))
+    freq = np.arange(0.01, 17.41, 0.01)
+    n = 50000
+    got = vfo.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n)
+    m = vfo_oracle.stretch_multiplier(n)
+    want = scalar.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n, variant=(0 if mode == 'X' else 1),
+                                            multiplier=m, n_threads=0)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert rel_err(got, want) < 1e-9
+    k = int(np.argmax(den))
+    fcut = np.sqrt(den[k - 1]) * 8.97866275 / 1e6
+    near = np.abs(freq - fcut) < 0.05
+    assert near.any()
+    print("config5 %s: %d finite rows, max rel err %.2e (near-cutoff rows: %.2e)" % (
+        mode, int(np.isfinite(want).sum()), rel_err(got, want), rel_err(got[near], want[near])))

@@ -31,7 +31,8 @@ def main():
     torch.cuda.synchronize()
     L.prhf_debug_trace_alloc(ctx.handle, n_tiles)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    flush.zero_()
+    if not os.environ.get('TRACE_NO_FLUSH'):
+        flush.zero_()
     pyrayhf_b200.vertical_forward_operator_batched(*t, 'X', 20000)
     out = np.zeros((n_tiles + 4096, 8), dtype=np.int64)
     L.prhf_debug_trace_read(ctx.handle, n_tiles, vp(out.ctypes.data))
