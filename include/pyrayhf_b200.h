@@ -108,6 +108,17 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
                     int mode, int isotropic, unsigned flags, double* mu_out, double* mup_out,
                     void* cuda_stream);
 
+/*
+ * Residual of the inversion objective on DEVICE buffers (replaces the arithmetic tail of residual_VH,
+ * library.py:660-668, for a batch of candidate profiles): NaN model heights are replaced by
+ * max(nanmean|vh_model[p,:]|, 100) (library.py:664-665), residual = vh_obs - vh_model (library.py:668).
+ *   vh_model [n_profiles x n_freq], vh_obs [n_freq]
+ *   residual_out [n_profiles x n_freq] (may be NULL), chi2_out [n_profiles] = sum of squared residuals, the
+ *   quantity lmfit's brute-force search minimises at library.py:794-798 (may be NULL).
+ */
+int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_obs, int64_t n_profiles, int n_freq,
+                      double* residual_out, double* chi2_out, void* cuda_stream);
+
 /* Device FP64 FMA throughput probe used for the roofline denominator: runs a dependent-free DFMA
  * kernel and returns the measured TFLOP/s (2 flop per FMA). */
 int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out);

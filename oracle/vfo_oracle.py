@@ -193,6 +193,18 @@ def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O',
     return out
 
 
+def residual_from_model(vh_obs, vh_model):
+    """Arithmetic tail of residual_VH: NaN fill and difference.  library.py:660-668.
+
+    ``vh_model`` is one modelled curve [F] (as in the reference) or a batch [P, F] (row-wise).
+    """
+    vh_model = np.array(vh_model, dtype=float, copy=True)
+    if vh_model.ndim == 1:
+        vh_model[np.isnan(vh_model)] = np.maximum(np.nanmean(np.abs(vh_model)), 100)   # library.py:664-665
+        return (vh_obs - vh_model).ravel()                                               # library.py:668
+    return np.stack([residual_from_model(vh_obs, row) for row in vh_model])
+
+
 def profile_status(den):
     """0 ok / 1 negative density below the peak / 2 peak at index 0.
 

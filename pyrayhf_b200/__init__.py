@@ -17,6 +17,8 @@ from pyrayhf_b200.library import (  # noqa: E402,F401
     vertical_forward_operator,
     vertical_forward_operator_batched,
     find_mu_mup,
+    residual_VH_batched,
+    brute_force_fit,
     install,
     uninstall,
 )

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "prhf_version", "prhf_error_string", "prhf_last_cuda_error", "prhf_ctx_create",
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
     "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
-    "prhf_selftest_math", "prhf_kernel_timing",
+    "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64",
 )
 
 _vp = ctypes.c_void_p
@@ -89,6 +89,8 @@ def load():
         L.prhf_kernel_timing.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(_i)]
         L.prhf_kernel_timing.restype = _i
+        L.prhf_residual_f64.argtypes = [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]
+        L.prhf_residual_f64.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L

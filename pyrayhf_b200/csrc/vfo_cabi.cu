@@ -661,6 +661,18 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
   return PRHF_OK;
 }
 
+int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_obs, int64_t n_profiles, int n_freq,
+                      double* residual_out, double* chi2_out, void* cuda_stream) {
+  if (!ctx || n_profiles < 0 || n_freq < 0) return PRHF_ERR_INVALID_ARG;
+  if (n_profiles == 0 || n_freq == 0) return PRHF_OK;
+  if (!vh_model || !vh_obs || (!residual_out && !chi2_out)) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_residual(vh_model, vh_obs, n_profiles, n_freq, residual_out, chi2_out,
+                                       (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
 int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err6) {
   if (!ctx || !max_rel_err6) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);

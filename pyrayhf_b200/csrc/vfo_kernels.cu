@@ -1275,6 +1275,43 @@ __global__ void mu_mup_kernel(const double* __restrict__ X, const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// residual of the inversion objective (residual_VH, lib:660-668): NaN model heights are replaced by
+// max(nanmean|vh_model|, 100) (lib:664-665), residual = vh_obs - vh_model (lib:668); chi2 = sum residual^2 is
+// what lmfit's brute-force search minimises (lib:794-798).  One warp per candidate profile.
+// ------------------------------------------------------------------------------------------
+__global__ void residual_kernel(const double* __restrict__ vh, const double* __restrict__ vh_obs, int64_t n_profiles,
+                                int n_freq, double* __restrict__ residual, double* __restrict__ chi2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pr = warp; pr < n_profiles; pr += n_warps) {
+    const double* row = vh + pr * n_freq;
+    double s = 0.0;
+    int cnt = 0;
+    for (int k = lane; k < n_freq; k += 32) {
+      const double v = row[k];
+      if (v == v) { s += fabs(v); ++cnt; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    // np.nanmean of an all-NaN row is NaN and np.maximum(NaN, 100) is NaN: the whole residual is NaN
+    const double fill = (cnt > 0) ? fmax(s / (double)cnt, 100.0) : CUDART_NAN;
+    double c = 0.0;
+    for (int k = lane; k < n_freq; k += 32) {
+      const double v = row[k];
+      const double r = vh_obs[k] - ((v == v) ? v : fill);
+      if (residual) residual[pr * n_freq + k] = r;
+      c = fma(r, r, c);
+    }
+    c = warp_sum(c);
+    if (lane == 0 && chi2) chi2[pr] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 FMA throughput probe (roofline denominator)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double seed) {
@@ -1466,6 +1503,15 @@ cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, i
   else if (literal) PRHF_LAUNCH(1, true, false);
   else PRHF_LAUNCH(1, false, false);
 #undef PRHF_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
+                            double* chi2, cudaStream_t stream) {
+  if (n_profiles <= 0) return cudaSuccess;
+  int64_t blocks = (n_profiles + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  residual_kernel<<<(unsigned)blocks, 256, 0, stream>>>(vh, vh_obs, n_profiles, n_freq, residual, chi2);
   return cudaGetLastError();
 }
 

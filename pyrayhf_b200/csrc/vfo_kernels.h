@@ -98,6 +98,8 @@ cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_i
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
+cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
+                            double* chi2, cudaStream_t stream);
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_math_selftest(int n, double* err2, cudaStream_t stream);
 

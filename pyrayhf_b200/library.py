@@ -218,6 +218,63 @@ def find_mu_mup(X, Y, bpsi, mode, *, y_tol=1e-12, literal=False):
     return mu.cpu().numpy().reshape(shape), mup.cpu().numpy().reshape(shape)
 
 
+def residual_VH_batched(vh_obs, vh_model, *, return_residual=True):
+    """Residuals of a batch of modelled virtual-height curves against one observed curve.
+
+    The arithmetic tail of ``residual_VH`` (library.py:660-668) for ``vh_model`` of shape ``[P, F]``:
+    NaN model heights become ``max(nanmean(|vh_model[p]|), 100)`` (library.py:664-665) and
+    ``residual[p] = vh_obs - vh_model[p]`` (library.py:668).  Returns ``(residual [P, F], chi2 [P])`` with
+    ``chi2 = sum(residual**2, axis=1)``, the quantity the brute-force search minimises
+    (library.py:794-798).  float64 CUDA tensors in -> tensors out (asynchronous); numpy in -> numpy out.
+    """
+    import torch
+    is_t = _is_torch_tensor(vh_model)
+    if is_t:
+        dev = vh_model.device
+        vm = vh_model.contiguous()
+        vo = vh_obs.to(dev).contiguous() if _is_torch_tensor(vh_obs) else torch.from_numpy(_f64(vh_obs)).to(dev)
+    else:
+        dev = torch.device('cuda', torch.cuda.current_device())
+        vm = torch.from_numpy(_f64(vh_model)).to(dev)
+        vo = torch.from_numpy(_f64(vh_obs).reshape(-1)).to(dev)
+    if vm.dim() != 2 or vo.numel() != vm.shape[1]:
+        raise ValueError("vh_model must be [P, F] and vh_obs [F]")
+    n_prof, n_freq = vm.shape
+    res = torch.empty_like(vm) if return_residual else None
+    chi2 = torch.empty(n_prof, dtype=torch.float64, device=dev)
+    ctx = _cabi.context(dev.index)
+    rc = ctx.lib.prhf_residual_f64(ctx.handle, _vp(vm.data_ptr()), _vp(vo.data_ptr()), n_prof, n_freq,
+                                   _vp(res.data_ptr()) if res is not None else None, _vp(chi2.data_ptr()),
+                                   _vp(torch.cuda.current_stream(dev).cuda_stream))
+    ctx.check(rc)
+    if is_t:
+        return res, chi2
+    return (res.cpu().numpy() if res is not None else None), chi2.cpu().numpy()
+
+
+def brute_force_fit(freq, vh_obs, den_candidates, bmag, bpsi, alt, mode='O', n_points=200):
+    """Score a batch of candidate electron-density profiles against observed virtual heights.
+
+    What ``minimize_parameters`` (library.py:672-825) does per grid node of its brute-force search --
+    build a profile, run the forward operator, form the residual -- for ``den_candidates`` ``[P, A]`` supplied
+    by the caller (the PyIRI profile builder of library.py:557-583 is not available offline).  ``bmag`` /
+    ``bpsi`` are ``[A]`` (shared) or ``[P, A]``.  Returns ``(best_index, chi2 [P], vh_model [P, F])``; failed
+    candidates (negative density, peak at the bottom) score NaN.
+    """
+    den = _f64(den_candidates)
+    n_prof = den.shape[0]
+    bm = _f64(bmag)
+    bp = _f64(bpsi)
+    if bm.ndim == 1:
+        bm = np.ascontiguousarray(np.broadcast_to(bm, den.shape))
+    if bp.ndim == 1:
+        bp = np.ascontiguousarray(np.broadcast_to(bp, den.shape))
+    vh = vertical_forward_operator_batched(freq, den, bm, bp, alt, mode, n_points, errors='nan')
+    _, chi2 = residual_VH_batched(vh_obs, vh, return_residual=False)
+    best = int(np.nanargmin(chi2)) if np.isfinite(chi2).any() else -1
+    return best, chi2, vh
+
+
 _saved = {}
 
 

@@ -358,3 +358,47 @@ def test_config5_frequency_sweep_full_size(vfo, golden, mode):
     assert near.any()
     print("config5 %s: %d finite rows, max rel err %.2e (near-cutoff rows: %.2e)" % (
         mode, int(np.isfinite(want).sum()), rel_err(got, want), rel_err(got[near], want[near])))
+
+
+def test_residual_objective(vfo):
+    """prhf_residual_f64 (tail of residual_VH, lib:660-668) against its numpy restatement, and the batched
+    brute-force scoring built on it."""
+    import torch
+    rng = np.random.default_rng(11)
+    n_prof, n_freq = 300, 37
+    vh_obs = 200.0 + 100.0 * rng.random(n_freq)
+    vh = 150.0 + 200.0 * rng.random((n_prof, n_freq))
+    vh[rng.random((n_prof, n_freq)) < 0.25] = np.nan
+    vh[7] = np.nan                                            # all-NaN row: nanmean is NaN, residual all NaN
+    vh[8] = 50.0                                              # finite, mean below 100 (fill unused)
+    vh[9, ::2] = np.nan
+    vh[9, 1::2] = 20.0                                        # mean 20 -> fill 100
+    want = vfo_oracle.residual_from_model(vh_obs, vh)
+    res, chi2 = vfo.residual_VH_batched(vh_obs, vh)
+    assert np.array_equal(np.isnan(res), np.isnan(want))
+    # the NaN fill is a mean (different summation order on the GPU: last-ulp differences), and residuals are
+    # differences of ~300 km numbers: compare absolutely
+    m = np.isfinite(want)
+    assert np.max(np.abs(res[m] - want[m])) < 1e-10
+    np.testing.assert_allclose(chi2[np.isfinite(chi2)], np.sum(want ** 2, axis=1)[np.isfinite(chi2)], rtol=1e-10)
+    assert np.isnan(chi2[7]) and np.all(np.isnan(res[7]))
+    # torch in / torch out
+    dev = torch.device("cuda:0")
+    r2, c2 = vfo.residual_VH_batched(torch.from_numpy(vh_obs).to(dev), torch.from_numpy(vh).to(dev))
+    assert np.array_equal(r2.cpu().numpy(), res, equal_nan=True) and np.array_equal(c2.cpu().numpy(), chi2, equal_nan=True)
+    # brute-force scoring: the candidate that generated the observations must win with chi2 == 0
+    alt = synth.default_alt()
+    freq = np.arange(2.0, 9.0, 0.25)
+    fof2 = np.linspace(8.0, 12.0, 9)
+    hmf2 = np.linspace(280.0, 340.0, 7)
+    ff, hh = np.meshgrid(fof2, hmf2, indexing="ij")
+    den, bmag, bpsi = synth.profiles_from_parameters(ff.ravel(), hh.ravel(), np.full(ff.size, 50.0),
+                                                     np.full(ff.size, 3.0), np.full(ff.size, 20.0), alt)
+    truth_idx = 31
+    obs = vfo.vertical_forward_operator(freq, den[truth_idx], bmag[truth_idx], bpsi[truth_idx], alt, 'O', 200)
+    assert np.all(np.isfinite(obs))
+    best, chi2, vh_all = vfo.brute_force_fit(freq, obs, den, bmag[0], bpsi[0], alt, 'O', 200)
+    assert best == truth_idx and chi2[truth_idx] == 0.0
+    assert vh_all.shape == (ff.size, freq.size)
+    ref_chi2 = np.sum(vfo_oracle.residual_from_model(obs, vh_all) ** 2, axis=1)
+    np.testing.assert_allclose(chi2, ref_chi2, rtol=1e-9, atol=1e-12)

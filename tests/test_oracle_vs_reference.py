@@ -84,3 +84,25 @@ def test_install_rebinds_reference_global(ref):
     finally:
         pyrayhf_b200.uninstall()
     assert ref.vertical_forward_operator is original
+
+
+def test_residual_tail_matches_reference_residual_VH(ref):
+    """oracle.residual_from_model against the reference's residual_VH with model_VH patched to return a given
+    curve (the reference's own tests patch the same module globals, tests/test_core.py:345-349)."""
+    from unittest.mock import patch
+
+    class P:                                            # minimal stand-in for lmfit.Parameters entries
+        def __init__(self, v):
+            self.value = v
+
+    params = {"NmF2": P(1e12), "hmF2": P(300.0), "B_bot": P(40.0)}
+    F2 = {"Nm": np.array([[1e12]]), "hm": np.array([[300.0]]), "B_bot": np.array([[40.0]])}
+    rng = np.random.default_rng(3)
+    vh_obs = 200.0 + 100.0 * rng.random(12)
+    for frac_nan in (0.0, 0.3, 1.0):
+        vh_model = 150.0 + 200.0 * rng.random(12)
+        vh_model[rng.random(12) < frac_nan] = np.nan
+        with patch("PyRayHF.library.model_VH", return_value=(vh_model.copy(), None)):
+            want = ref.residual_VH(params, F2, {}, {}, np.arange(12.0), vh_obs, None, None, None)
+        got = vfo_oracle.residual_from_model(vh_obs, vh_model)
+        assert np.array_equal(want, got, equal_nan=True)
