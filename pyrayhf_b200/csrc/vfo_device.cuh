@@ -2,10 +2,10 @@
 //
 // Reference behaviour being replaced (PyRayHF/library.py, "lib"):
 //   lib:120-158  find_X / find_Y            -> x_literal / y_literal and the per-row scale factors
-//   lib:161-256  find_mu_mup                -> ah_literal (operation by operation) and ah_fast
-//   lib:424-426  np.interp of den/bmag/bpsi -> interp_numpy (numpy arr_interp semantics) / fma form
+//   lib:161-256  find_mu_mup                -> ah_literal (operation by operation), ah_fast (sign-safe), ah_hot (hot loop)
+//   lib:424-426  np.interp of den/bmag/bpsi -> point_term in vfo_kernels.cu (numpy arr_interp semantics) / fma form
 //
-// Tensor cores are not used: the path is ~90 dependent FP64 scalar operations per grid point with
+// Tensor cores are not used: the path is ~50 dependent FP64 scalar operations per grid point with
 // no contraction structure; it is bounded by the FP64 pipe (DESIGN.md "Roofline").
 #pragma once
 #include <cuda_runtime.h>
@@ -28,22 +28,6 @@ __device__ __forceinline__ double x_literal(double den, double f_hz) {
 }
 __device__ __forceinline__ double y_literal(double b, double f_hz) {
   return __ddiv_rn(__dmul_rn(kGp, b), f_hz);
-}
-
-// ---- numpy arr_interp for one query whose bracket j (last xp[j] <= x, -1 below, n above) is known ----
-__device__ __forceinline__ double interp_numpy(double x, int j, int n, const double* xp, const double* fp,
-                                               const double* slope) {
-  if (n == 1 || j < 0) return fp[0];
-  if (j >= n - 1) return fp[n - 1];
-  const double xj = xp[j];
-  if (xj == x) return fp[j];
-  const double s = slope[j];
-  double r = __dadd_rn(__dmul_rn(s, __dsub_rn(x, xj)), fp[j]);
-  if (isnan(r)) {
-    r = __dadd_rn(__dmul_rn(s, __dsub_rn(x, xp[j + 1])), fp[j + 1]);
-    if (isnan(r) && fp[j] == fp[j + 1]) r = fp[j];
-  }
-  return r;
 }
 
 // ---- lib:209-254, every operation in the reference's order (IEEE div / sqrt, libdevice sincos) ----
@@ -154,56 +138,13 @@ __device__ __forceinline__ double ah_fast(double X, double Y, double sn, double 
   return mup;
 }
 
-// ---- the same formulas with the reciprocal folded into the second reciprocal square root ----
-// Used for every grid point of a row that reflects above the first level (the hot loop).
+// ---- hot-loop form: the reciprocal of D folded into the second reciprocal square root ----
+// Used for every grid point of a row that reflects above the first level.
 //   X-mode:  E = D - X Xm1 (= D mu^2), rs = 1/sqrt(D E):  mu = |E rs|, 1/D = (E rs) rs,
 //            1/(D mu) = copysign(rs, E rs)           -- exact for either sign of D
 //   O-mode:  N = Xm1 P + w, G = P + w, mu^2 = N/G, rs = 1/sqrt(Xm1^2 N G):  mu = Xm1 N rs,
 //            1/G = (Xm1 N rs)(Xm1 rs), q = X P / G, 1/(D mu) = P rs   -- assumes Xm1 > 0, which holds at
 //            every grid point below the X = 1 reflection level (rows that start above it take ah_fast)
-// 41 (X) / 42 (O) FP64 instructions per point including both reciprocal square roots.
-template <int MODE>
-__device__ __forceinline__ double ah_core(double X, double Y, double sn, double cs) {
-  const double YT = Y * sn, YL = Y * cs;
-  const double Xm1 = 1.0 - X;
-  const double a = 0.5 * (YT * YT);
-  const double w = (YL * YL) * Xm1;
-  const double a2 = a * a;
-  const double alpha = fma(w, Xm1, a2);
-  const double rb = rsqrt_fast(alpha);
-  const double beta = alpha * rb;
-  const double P = a + beta;
-  const double two_a = a + a;
-  double mu, c, q, dDdX, YdDdY;
-  if (MODE == 1) {
-    const double D = Xm1 - P;
-    const double XX = X * Xm1;
-    const double E = D - XX;
-    const double rs = rsqrt_fast(D * E);
-    const double t1 = E * rs;
-    mu = fabs(t1);
-    q = XX * (t1 * rs);
-    c = copysign(rs, t1);
-    dDdX = fma(w, rb, -1.0);
-    YdDdY = -fma(a2, rb, beta) - two_a;
-  } else {
-    const double N = fma(Xm1, P, w);
-    const double G = P + w;
-    const double z = Xm1 * N;
-    const double rs = rsqrt_fast(z * (Xm1 * G));
-    const double v = z * rs;
-    mu = fabs(v);
-    q = (X * P) * (v * (Xm1 * rs));
-    c = P * rs;
-    dDdX = -fma(w, rb, 1.0);
-    YdDdY = fma(a2, rb, beta) - two_a;
-  }
-  const double br = fma(0.5 * q, YdDdY, X * fma(q, dDdX, fma(2.0, X, -1.0)));
-  const double mup = fma(-c, br, mu);
-  return (mu <= 1.0) ? mup : CUDART_NAN;               // lib:233 (NaN mu) and lib:238
-}
-
-// ---- hot-loop form of ah_core ----
 // Inputs: YTh = Y sin(psi) / sqrt(2) (so that a = YTh^2), YL = Y cos(psi).  Returns mu' and mu; the caller
 // tests validity (mu <= 1, not NaN) on the bit patterns with integer instructions, keeping compares off the
 // FP64 pipe.  36 (X) / 37 (O) FP64 instructions.

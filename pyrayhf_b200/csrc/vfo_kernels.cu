@@ -686,11 +686,11 @@ enum : int {
   kPathIso = 5       // unmagnetised branch (lib:202-206), numpy-literal interpolation
 };
 
-// mu' * dh for one grid point (NaN -> 0 handled by the caller).
+// mu' * dh for one grid point on the general / literal / isotropic paths (NaN -> 0 handled by the caller).
 template <int MODE, int PATH>
 __device__ __forceinline__ double point_term(double h, double dh, int j, const Node* nodes, const RowConst& rc) {
   double mup;
-  if (PATH >= kPathGeneral) {
+  {
     // numpy arr_interp semantics (NaN rescue, exact-node shortcut, clamping) on the staged window;
     // node fields hold raw density / field / angle[deg] and their slopes here
     const int jj = max(j, rc.jlo) - rc.jlo;
@@ -739,16 +739,6 @@ __device__ __forceinline__ double point_term(double h, double dh, int j, const N
         mup = ah_fast<MODE>(X, Y, sn, cs, nullptr);
       }
     }
-  } else {
-    // Rows on this path reflect above the first level, so alt0 <= h and jlo <= j <= jhi.
-    const Node& nd = nodes[j - rc.jlo];
-    const double t = h - nd.alt;
-    const double X = fma(nd.sx, t, nd.x);
-    const double Y = fma(nd.sy, t, nd.y);
-    double sn = nd.sn, cs = nd.cs;
-    if (PATH == kPathFastS) rotate_sincos_small(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
-    if (PATH == kPathFastL) rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
-    mup = ah_core<MODE>(X, Y, sn, cs);
   }
   return mup * dh;                                                   // lib:288
 }
@@ -777,7 +767,6 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
       const int g0 = __double2int_rd((h0 - rc.alt0) * rc.inv_dalt);
       int j0 = find_bracket(h0, nodes, rc.jlo, rc.jhi, g0);
       int j1 = find_bracket(h1, nodes, rc.jlo, rc.jhi, j0);
-      if (PATH < kPathGeneral) { j0 = max(j0, rc.jlo); j1 = max(j1, rc.jlo); }
       t0 = point_term<MODE, PATH>(h0, dh0, j0, nodes, rc);
       t1 = point_term<MODE, PATH>(h1, dh1, j1, nodes, rc);
     }
@@ -1137,6 +1126,14 @@ template <int MODE, bool LITERAL>
 __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(const VfoParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockScratch sc;
+  // While the row-setup grid is still running (PDL): pull the multiplier table into L2.  It does not depend
+  // on K1, and after an L2 flush its first touch would otherwise be a DRAM miss inside the grid loop.
+  if (p.live_count != nullptr) {
+    const size_t bytes = sizeof(double) * (size_t)(p.n_points + kMultPad);
+    for (size_t off = ((size_t)blockIdx.x * kTileThreads + threadIdx.x) * 128; off < bytes;
+         off += (size_t)gridDim.x * kTileThreads * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.mult) + off));
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");      // the row-setup grid has completed (no-op without PDL)
   if (p.live_count == nullptr) {
     const int64_t tile = blockIdx.x;

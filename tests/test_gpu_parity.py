@@ -402,3 +402,50 @@ def test_residual_objective(vfo):
     assert vh_all.shape == (ff.size, freq.size)
     ref_chi2 = np.sum(vfo_oracle.residual_from_model(obs, vh_all) ** 2, axis=1)
     np.testing.assert_allclose(chi2, ref_chi2, rtol=1e-9, atol=1e-12)
+
+
+def test_config3_global_grid_full_size(vfo):
+    """BASELINE configs[2]: the 181 x 361 one-degree grid (65,341 profiles), O and X mode, 174 frequencies,
+    n_points = 200, as CUDA tensors.  Checked through size-independent properties (no status errors, determinism,
+    each sampled row equals the single-profile call bit for bit) and against the oracle on sampled profiles."""
+    import torch
+    lat, lon = synth.global_grid_points()
+    alt = synth.default_alt()
+    freq = synth.default_freq()
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    assert den.shape == (65341, 620)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+    rng = np.random.default_rng(5)
+    sample = np.concatenate([[0, 180, 65340, 32670], rng.integers(0, 65341, 12)])
+    for mode in "OX":
+        vh, st = vfo.vertical_forward_operator_batched(*t, mode, 200, return_status=True)
+        assert int(st.abs().sum().item()) == 0
+        a = vh.cpu().numpy()
+        b = vfo.vertical_forward_operator_batched(*t, mode, 200).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True)
+        assert np.nanmin(a) >= alt[0] and np.isfinite(a).mean() > 0.2
+        m = vfo_oracle.stretch_multiplier(200)
+        for p in sample:
+            ref = vfo_oracle.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, mode, 200)
+            tru = scalar.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, mode, 200, variant=1,
+                                                   multiplier=m)
+            assert_parity(a[p], ref, tru, mode, "config3 profile %d" % p)
+
+
+def test_config4_ensemble_member_chunk(vfo):
+    """BASELINE configs[3] (1,024 members x 8,192 profiles, X-mode, n_points = 20000) is streamed member by
+    member; one member chunk of 1,024 perturbed profiles is run here and spot-checked against the oracle."""
+    import torch
+    lat, lon = synth.grid_subset(1024)
+    alt = synth.default_alt()
+    freq = synth.default_freq()
+    den, bmag, bpsi = synth.ensemble_member(lat, lon, member=3, alt=alt)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+    vh, st = vfo.vertical_forward_operator_batched(*t, 'X', 20000, return_status=True)
+    assert int(st.abs().sum().item()) == 0
+    a = vh.cpu().numpy()
+    for p in (0, 511, 1023):
+        ref = vfo_oracle.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, 'X', 20000)
+        assert np.array_equal(np.isnan(a[p]), np.isnan(ref)) and rel_err(a[p], ref) < 1e-9

@@ -1,6 +1,6 @@
 #!/bin/bash
 # developer sweep over K2 block-size / occupancy variants (built with `make variant TT=.. MB=..`)
-for lib in libpyrayhf_b200.so libpyrayhf_b200_t256_b4.so libpyrayhf_b200_t128_b6.so; do
+for lib in libpyrayhf_b200.so libpyrayhf_b200_t256_b4.so libpyrayhf_b200_t128_b6.so libpyrayhf_b200_t128_b8.so; do
   export PRHF_LIB_PATH=$PWD/pyrayhf_b200/csrc/$lib
   [ -f $PRHF_LIB_PATH ] || continue
   a=$(python bench.py --steps 30 --warmup 5 --no-cpu-baseline | python -c "
