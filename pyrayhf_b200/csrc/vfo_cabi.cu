@@ -57,6 +57,7 @@ struct prhf_ctx {
   bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
+  int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
@@ -266,6 +267,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_K1_LANES")) ctx->use_k1_lanes = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_PLAN_NSEG")) ctx->force_nseg = atoi(s);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
   DeviceGuard g(device);
@@ -377,6 +379,7 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     // candidate tilings: ns segments of a length that is a multiple of two points per thread
     const int quantum = 2 * prhf::kTileThreads;
     for (int ns = 1; ns <= n_seg && n_cand < prhf::kMaxPlanCand; ++ns) {
+      if (ctx->force_nseg > 0 && ns != ctx->force_nseg) continue;   // developer override (PRHF_PLAN_NSEG)
       const int sl = ((n_points + ns - 1) / ns + quantum - 1) / quantum * quantum;
       if ((n_points + sl - 1) / sl != ns) continue;           // rounding made a segment empty
       cand_seg[n_cand] = ns;
@@ -455,6 +458,8 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.use_pdl = ctx->use_pdl ? 1 : 0;
     P.max_seg = n_seg;
     P.slots = slots;
+    P.n_sm = ctx->sm_count;
+    P.ctas_per_sm = ctas_per_sm;
     P.n_cand = n_cand;
     for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;

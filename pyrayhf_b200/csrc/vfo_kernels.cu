@@ -1099,15 +1099,20 @@ template <int MODE, bool LITERAL>
 __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char* smem_raw, BlockScratch& sc) {
   const int live = (int)__ldcg(p.live_count);
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.live_count_other = 0u;   // consumed by the previous call
-  // cost model: waves * (per-tile overhead + points per tile * cycles per point at full occupancy)
+  // Cost model (SM cycles) for splitting every live row into ns segments of L points:
+  //   k = ceil(live * ns / n_sm) tiles land on the busiest SM; each costs L * cpp(resident CTAs) for its grid
+  //   points plus a fixed prologue/reduction overhead.  cpp: cycles per grid point of one SM with 1, 2, >= 3
+  //   resident tile CTAs (one CTA cannot hide the FP64 latency chain).  Constants fitted to the phase trace
+  //   (tools/trace_tiles.py) and the segment sweep in profiles/sweep_nseg_r01.log.
   int n_seg = 1, seg_len = p.n_points;
   {
     float best_cost = 3.0e38f;
-    const float inv_slots = 1.0f / (float)p.slots;
+    const float inv_sm = 1.0f / (float)p.n_sm;
     for (int c = 0; c < p.n_cand; ++c) {
-      const float tiles = (float)max(live, 1) * (float)p.cand_seg[c];
-      const float waves = ceilf(tiles * inv_slots - 1e-4f);
-      const float cost = waves * ((float)kPlanTileOverhead + (float)p.cand_len[c] * (float)kPlanCyclesPerPoint);
+      const float k = ceilf((float)max(live, 1) * (float)p.cand_seg[c] * inv_sm - 1e-4f);
+      const float resident = fminf(k, (float)p.ctas_per_sm);
+      const float cpp = (resident < 1.5f) ? kPlanCpp1 : ((resident < 2.5f) ? kPlanCpp2 : kPlanCpp3);
+      const float cost = k * ((float)p.cand_len[c] * cpp + kPlanTileOverhead);
       if (cost < best_cost) { best_cost = cost; n_seg = p.cand_seg[c]; seg_len = p.cand_len[c]; }
     }
   }

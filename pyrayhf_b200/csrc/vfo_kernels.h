@@ -44,8 +44,8 @@ struct __align__(16) LiveRow {    // planned mode: one entry per row that reflec
 };
 // planner cost model (SM cycles): per-tile prologue + reduction, and loop cycles per grid point of one
 // tile when the SM is fully occupied (measured with the developer phase trace, tools/trace_tiles.py)
-constexpr double kPlanTileOverhead = 2600.0;
-constexpr double kPlanCyclesPerPoint = 3.2;
+constexpr float kPlanTileOverhead = 3500.0f;
+constexpr float kPlanCpp1 = 2.6f, kPlanCpp2 = 1.45f, kPlanCpp3 = 1.35f;
 constexpr int kMaxPlanCand = 32;
 
 struct VfoParams {
@@ -82,6 +82,7 @@ struct VfoParams {
   unsigned* grid_bar;          // fused kernel: {arrive count, generation}, both self-maintaining
   int max_seg;             // stride of `partial` per row; planner's upper bound on n_seg
   int slots;               // resident tile-kernel CTAs on the device
+  int n_sm, ctas_per_sm;   // its factors
   int n_cand;              // planner candidates: (segments per row, grid points per segment)
   int cand_seg[kMaxPlanCand];
   int cand_len[kMaxPlanCand];
