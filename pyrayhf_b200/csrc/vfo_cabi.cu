@@ -53,15 +53,15 @@ struct prhf_ctx {
   long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
   size_t trace_k1_off = 0;           // K1 entries start here (in long longs)
   // planned mode (small batches): tile plan, compact tile list, K1 completion counter
-  unsigned* live_count = nullptr;    // [2] one per call parity, followed by the fused kernel's barrier words [2]
+  unsigned* live_count = nullptr;    // [0] live-row counter of planned mode, [2..3] the fused kernel's barrier words
   bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
+  bool use_solo = true;              // PRHF_NO_SOLO=1: single-profile calls through the two-kernel planned mode
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
   int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
-  int plan_parity = 0;
   // optional per-kernel timing (bench roofline): events around K1 and K2 of every launch pair
   bool kernel_timing = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -207,6 +207,21 @@ bool use_planned_mode(const prhf_ctx* ctx, int64_t rows_total, int n_points) {
   return ctx->seg_len_override <= 0 && rows_total <= (int64_t)ctx->planned_max_rows && n_points >= 2048;
 }
 
+// How a call is decomposed: solo (single launch, one profile), planned (small batch), else direct.
+struct CallMode {
+  bool solo, planned;
+  int slots, ctas_per_sm;
+};
+CallMode call_mode(const prhf_ctx* ctx, int64_t rows_total, int n_points, int n_alt) {
+  CallMode m;
+  m.ctas_per_sm = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm);
+  m.slots = ctx->sm_count * m.ctas_per_sm;
+  const bool small = use_planned_mode(ctx, rows_total, n_points);
+  m.solo = ctx->use_solo && small && rows_total * 2 <= m.slots;
+  m.planned = small && !m.solo;
+  return m;
+}
+
 int validate(const prhf_ctx* ctx, const void* freq, int n_freq, const void* den, const void* bmag, const void* bpsi,
              const void* alt, int64_t n_profiles, int n_alt, int mode, int n_points, const void* vh) {
   if (!ctx) return PRHF_ERR_INVALID_ARG;
@@ -265,6 +280,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_NO_GRAPH")) ctx->use_graphs = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_FUSED")) ctx->use_fused = (atoi(s) != 0);
   if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_NO_SOLO")) ctx->use_solo = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_K1_LANES")) ctx->use_k1_lanes = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_PLAN_NSEG")) ctx->force_nseg = atoi(s);
@@ -364,16 +380,25 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
 
   const int64_t rows_total = n_profiles * (int64_t)n_freq;
   const bool literal = (flags & PRHF_FLAG_LITERAL) != 0;
-  const int ctas_per_sm = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm);
-  const int slots = ctx->sm_count * ctas_per_sm;
+  const CallMode cm = call_mode(ctx, rows_total, n_points, n_alt);
+  const int ctas_per_sm = cm.ctas_per_sm, slots = cm.slots;
 
   // Small batches (fewer rows than a few waves of tiles): planned mode.  K1's last CTA counts the rows
   // that reflect and sizes the segments so that the live tiles fill the resident-CTA slots; K2 strides
   // over the compact tile list.  Large batches: direct mode, one tile per row.
-  const bool planned = use_planned_mode(ctx, rows_total, n_points);
+  // Single profile (rows * 2 <= resident CTAs): solo mode, one launch with a static split of every row.
+  const bool solo = cm.solo, planned = cm.planned;
   int seg_len = 0, n_seg = 0;
   int n_cand = 0, cand_seg[prhf::kMaxPlanCand] = {0}, cand_len[prhf::kMaxPlanCand] = {0};
-  if (planned) {
+  if (solo) {
+    const int quantum = 2 * prhf::kTileThreads;
+    int want = (int)std::min<int64_t>(slots / rows_total, std::max(1, n_points / 2048));
+    for (;; --want) {                                         // largest split whose segments are all non-empty
+      seg_len = ((n_points + want - 1) / want + quantum - 1) / quantum * quantum;
+      n_seg = (n_points + seg_len - 1) / seg_len;
+      if (n_seg == want || want <= 1) break;
+    }
+  } else if (planned) {
     n_seg = std::max(1, std::min(prhf::kMaxPlanCand, n_points / 1024));   // upper bound (stride of the partials)
     seg_len = n_points;                                       // unused by the kernels in planned mode
     // candidate tilings: ns segments of a length that is a multiple of two points per thread
@@ -434,7 +459,8 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_points = n_points;
     P.seg_len = seg_len;
     P.n_seg = n_seg;
-    P.rows_per_warp = rows_per_warp;
+    P.rows_per_warp = solo ? 1 : rows_per_warp;
+    P.k1_solo = solo ? 1 : 0;
     P.k1_lane_mode = (!planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count) ? 1 : 0;
     P.vh = vh_out;
     P.status = status;
@@ -444,13 +470,14 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.counter = ctx->counter;
     P.trace = ctx->trace;
     if (planned) {
-      P.live_count = ctx->live_count + ctx->plan_parity;
-      P.live_count_other = ctx->live_count + (1 - ctx->plan_parity);
+      // the live-row counter starts every launch at zero (a 4-byte memset node: simpler and safer than any
+      // hand-over of the reset between consecutive calls)
+      PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, sizeof(unsigned), stream));
+      P.live_count = ctx->live_count;
       P.live_list = ctx->live_list;
       P.grid_bar = ctx->live_count + 2;
-      ctx->plan_parity ^= 1;
     } else {
-      P.live_count = P.live_count_other = nullptr;
+      P.live_count = nullptr;
       P.live_list = nullptr;
       P.grid_bar = nullptr;
     }
@@ -463,6 +490,20 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_cand = n_cand;
     for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
+    if (solo) {
+      if (ctx->kernel_timing) PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_solo(P, mode, literal, np * tiles_per_profile, stream));
+      ctx->launches += 1;
+      if (ctx->kernel_timing) {                               // the one kernel counts as the "tile kernel"
+        PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+        PRHF_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
+        float b = 0.f;
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        ctx->k2_ms += b;
+        ctx->timed_pairs++;
+      }
+      continue;
+    }
     if (planned && ctx->use_fused && !ctx->kernel_timing) {
       // one cooperative launch: row setup, grid barrier, tiles
       const int rows_per_cta = prhf::kRowsPerCta * rows_per_warp;
@@ -601,14 +642,13 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
           if (ge.exec[k]) { cudaGraphExecDestroy(ge.exec[k]); ge.exec[k] = nullptr; }
         ge.calls = 0;
       }
-      const bool planned = use_planned_mode(ctx, np * (int64_t)n_freq, n_points);
-      const int parity = planned ? ctx->plan_parity : 0;
+      const int parity = 0;
       if (ge.calls >= 1) {
         if (!ge.exec[parity]) {
           cudaGraph_t graph = nullptr;
           if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
             const int64_t launches0 = ctx->launches;
-            rc = enqueue();                                    // flips plan_parity when planned
+            rc = enqueue();
             ge.n_launches = (int)(ctx->launches - launches0);
             ctx->launches = launches0;
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
@@ -616,7 +656,6 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
                 cudaGraphInstantiate(&ge.exec[parity], graph, 0) != cudaSuccess)
               ge.exec[parity] = nullptr;
             if (graph) cudaGraphDestroy(graph);
-            if (planned) ctx->plan_parity = parity;            // the captured call has not run yet
           }
           if (!ge.exec[parity]) {                              // capture is an optimisation, never a requirement
             cudaGetLastError();
@@ -625,7 +664,6 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
         }
         if (ge.exec[parity]) {
           PRHF_CUDA(ctx, cudaGraphLaunch(ge.exec[parity], ctx->stream));
-          if (planned) ctx->plan_parity ^= 1;
           ctx->launches += ge.n_launches;
           done = true;
         }

@@ -333,8 +333,10 @@ __device__ __noinline__ double dead_row_single_level(int mode, bool iso, double 
 }
 
 // `item` = (profile index inside the launch) * chunks + chunk of sounding frequencies.
+// Solo mode (p.k1_solo): the CTA belongs to ONE row (item = row index inside the launch); warp 0 scans it and
+// the outcome is also left in shared memory (*s_rec, *s_span) for the tile code that follows in the same CTA.
 __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, const int64_t item, double* smem,
-                                          BlockScratch& sc) {
+                                          BlockScratch& sc, ProfileRecord* s_rec, double* s_span) {
   const int A = p.n_alt;
   double* s_den = smem;
   double* s_alt = s_den + A;
@@ -343,7 +345,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   double* s_crit = s_psi + A;    // [kRowsPerCta][A]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows_per_cta = p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp;
+  const int rows_per_cta = p.k1_solo ? 1 : (p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp);
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   const int64_t lprof = item / chunks;                  // profile index inside this launch
   const int g = (int)(item % chunks);
@@ -431,7 +433,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     iso = (bmax == 0.0) || (__ddiv_rn(__dmul_rn(kGp, bmax), fmin_abs) < kYTol);
   }
 
-  if (g == 0 && tid == 0) {
+  if ((g == 0 || s_rec != nullptr) && tid == 0) {
     ProfileRecord rec;
     rec.nt = nt;
     rec.flags = (iso ? kFlagIso : 0) | (any_general ? kFlagGeneral : 0) | (status ? kFlagFailed : 0) |
@@ -442,8 +444,11 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     rec.alt0 = alt0;
     sincos(s_psi[0] * kDeg2Rad, &rec.sn0, &rec.cs0);
     rec.pad[0] = rec.pad[1] = 0.0;
-    p.prof_rec[lprof] = rec;
-    if (p.status) p.status[prof] = status;
+    if (s_rec) *s_rec = rec;
+    if (g == 0) {
+      p.prof_rec[lprof] = rec;
+      if (p.status) p.status[prof] = status;
+    }
   }
   PRHF_TRACE_K1(3);
   // ---- lane-per-row scan (large batches): thread t takes sounding frequency g * 256 + t ----
@@ -549,8 +554,8 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
   double* crit = s_crit + (size_t)wid * A;
   for (int rr = 0; rr < p.rows_per_warp; ++rr) {
-    const int r = (g * p.rows_per_warp + rr) * kRowsPerCta + wid;
-    if (r >= p.n_freq) break;
+    const int r = p.k1_solo ? g : (g * p.rows_per_warp + rr) * kRowsPerCta + wid;
+    if (r >= p.n_freq || (p.k1_solo && (wid != 0 || rr != 0))) break;
     const int64_t out_idx = prof * p.n_freq + r;
     const int64_t lrow = lprof * p.n_freq + r;
     if (status != 0) {
@@ -609,6 +614,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
       const double span = __dsub_rn(hc, s_alt[0]);          // lib:413 (h_c - aalt[0])
       p.row_span[lrow] = span;
+      if (s_span) *s_span = span;
       if (p.live_count) {                                   // planned mode: compact list of rows that reflect
         LiveRow e;
         e.row = (int)lrow;
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, c
   // Programmatic dependent launch: the tile kernel may be scheduled as soon as every CTA of this grid has
   // started; it blocks in griddepcontrol.wait until this grid has completed and its writes are visible.
   asm volatile("griddepcontrol.launch_dependents;");
-  rows_body(p, mode, blockIdx.x, smem, sc);
+  rows_body(p, mode, blockIdx.x, smem, sc, nullptr, nullptr);
 }
 
 // ==========================================================================================
@@ -977,9 +983,9 @@ __device__ __forceinline__ ProfileRecord load_profile_record(const ProfileRecord
 
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
-__device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span, const int seg,
-                                          const int n_seg, const int seg_len, unsigned char* smem_raw,
-                                          BlockScratch& sc) {
+__device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
+                                          const ProfileRecord* rec_src, const int seg, const int n_seg,
+                                          const int seg_len, unsigned char* smem_raw, BlockScratch& sc) {
   const int tid = threadIdx.x;
 #ifdef PRHF_TRACE
   if (p.trace && tid == 0) {
@@ -994,7 +1000,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int i0 = seg * seg_len;
   const int i1 = min(p.n_points, i0 + seg_len);
   // every load of the prologue is independent of the others: issue them together
-  const ProfileRecord rec = load_profile_record(p.prof_rec + lprof);
+  const ProfileRecord rec = rec_src ? *rec_src : load_profile_record(p.prof_rec + lprof);
   const double f_mhz = p.freq[prof * p.freq_stride + r];
   const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
   if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
@@ -1098,7 +1104,6 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char* smem_raw, BlockScratch& sc) {
   const int live = (int)__ldcg(p.live_count);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.live_count_other = 0u;   // consumed by the previous call
   // Cost model (SM cycles) for splitting every live row into ns segments of L points:
   //   k = ceil(live * ns / n_sm) tiles land on the busiest SM; each costs L * cpp(resident CTAs) for its grid
   //   points plus a fixed prologue/reduction overhead.  cpp: cycles per grid point of one SM with 1, 2, >= 3
@@ -1122,7 +1127,7 @@ __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char*
     // written earlier in this launch sequence (possibly in this very kernel): bypass L1
     const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
     const double span = __hiloint2double(raw.w, raw.z);
-    tile_body<MODE, LITERAL>(p, raw.x, span, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
+    tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
     __syncthreads();                                      // shared memory is reused by the next tile
   }
 }
@@ -1143,7 +1148,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
   if (p.live_count == nullptr) {
     const int64_t tile = blockIdx.x;
     const int64_t lrow = tile / p.n_seg;
-    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
+    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], nullptr, (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
     return;
   }
   planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
@@ -1218,6 +1223,26 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
   }
 }
 
+// Solo form for a single profile (rows * n_seg <= resident CTAs): ONE launch, no hand-off through global
+// memory.  Every CTA owns one tile = (row, segment), runs the row setup for its own row first (the segments of
+// a row repeat it, in parallel) and goes straight on to its grid points.  Removes the serial row-setup kernel
+// and the inter-kernel gap from the latency-critical single-profile call.
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_solo_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  __shared__ ProfileRecord s_rec;
+  __shared__ double s_span;
+  const int64_t tile = blockIdx.x;
+  const int64_t lrow = tile / p.n_seg;
+  if (threadIdx.x == 0) s_span = CUDART_NAN;
+  rows_body(p, MODE, lrow, reinterpret_cast<double*>(smem_raw), sc, &s_rec, &s_span);   // syncs internally
+  __syncthreads();
+  const double span = s_span;
+  if (!(span == span)) return;                            // no reflection / failed profile: NaN already written
+  tile_body<MODE, LITERAL>(p, lrow, span, &s_rec, (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
+}
+
 // Fused form of the planned mode (small batches), launched cooperatively with one wave of CTAs: the row
 // setup (K1) and the tiles (K2) run in ONE kernel separated by a grid-wide barrier, which removes the
 // second launch and the inter-kernel drain/fill from the latency-critical single-profile path.
@@ -1246,7 +1271,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_fused_kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockScratch sc;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    rows_body(p, MODE, item, reinterpret_cast<double*>(smem_raw), sc);
+    rows_body(p, MODE, item, reinterpret_cast<double*>(smem_raw), sc, nullptr, nullptr);
     __syncthreads();
   }
   grid_barrier(p.grid_bar);
@@ -1374,7 +1399,7 @@ size_t vfo_smem_bytes(int n_alt) {
 // cudaFuncSetAttribute costs ~1-2 us of host time per call; remember the largest size already granted per
 // (device, kernel) so that steady-state launches skip it (also keeps it out of stream capture).
 static cudaError_t grant_dynamic_smem(const void* func, int slot, size_t smem) {
-  static size_t granted[64][8] = {};
+  static size_t granted[64][20] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
@@ -1474,6 +1499,24 @@ static cudaError_t launch_fused_t(const VfoParams& p, int n_items, int max_grid,
   int items = n_items;
   void* args[] = {(void*)&pc, (void*)&items};
   return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kTileThreads), args, smem, stream);
+}
+
+template <int MODE, bool LITERAL>
+static cudaError_t launch_solo_t(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
+  static_assert(kTileThreads == kThreads, "the solo kernel runs the row setup with the tile kernel's block size");
+  const size_t a = sizeof(double) * 5 * (size_t)p.n_alt, b = vfo_tile_smem_bytes(p.n_alt);
+  const size_t smem = a > b ? a : b;
+  auto kern = vfo_solo_kernel<MODE, LITERAL>;
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 13 + MODE * 2 + (LITERAL ? 1 : 0), smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream) {
+  if (mode == 0)
+    return literal ? launch_solo_t<0, true>(p, n_tiles, stream) : launch_solo_t<0, false>(p, n_tiles, stream);
+  return literal ? launch_solo_t<1, true>(p, n_tiles, stream) : launch_solo_t<1, false>(p, n_tiles, stream);
 }
 
 cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,

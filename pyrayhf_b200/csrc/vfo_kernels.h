@@ -64,6 +64,7 @@ struct VfoParams {
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
   int rows_per_warp;       // K1: sounding frequencies handled by one warp (CTA = 8 warps)
+  int k1_solo;             // row setup inside the solo kernel: one row per CTA, scanned by warp 0
   int k1_lane_mode;        // K1: one thread per sounding frequency (large batches) instead of one warp
   int rw_rows_per_cta;     // row-per-warp kernel: rows of one profile handled by one CTA
   double* vh;              // [P x n_freq]
@@ -74,8 +75,7 @@ struct VfoParams {
   unsigned* counter;       // [rows_in_launch], zero on entry, zero on exit
   long long* trace;        // developer phase trace [tiles x 8] (PRHF_TRACE builds), else null
   // planned mode (small batches); null in direct mode
-  unsigned* live_count;        // zero on entry; K1 appends, K2 reads
-  unsigned* live_count_other;  // the other call parity's counter: K2 zeroes it for the next call
+  unsigned* live_count;        // zeroed by a memset node before K1; K1 appends, K2 reads
   LiveRow* live_list;          // [rows_in_launch]
   int64_t rows_in_launch;
   int use_pdl;                 // launch the tile kernel with programmatic stream serialization
@@ -94,6 +94,7 @@ int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
+cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);

@@ -350,7 +350,8 @@ def test_config5_frequency_sweep_full_size(vfo, golden, mode):
     m = vfo_oracle.stretch_multiplier(n)
     want = scalar.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n, variant=(0 if mode == 'X' else 1),
                                             multiplier=m, n_threads=0)
-    assert np.array_equal(np.isnan(got), np.isnan(want))
+    bad = np.flatnonzero(np.isnan(got) != np.isnan(want))
+    assert bad.size == 0, "mask mismatch at rows %s: got %s want %s" % (bad[:8], got[bad[:8]], want[bad[:8]])
     assert rel_err(got, want) < 1e-9
     k = int(np.argmax(den))
     fcut = np.sqrt(den[k - 1]) * 8.97866275 / 1e6
@@ -449,3 +450,35 @@ def test_config4_ensemble_member_chunk(vfo):
     for p in (0, 511, 1023):
         ref = vfo_oracle.vertical_forward_operator(freq, den[p], bmag[p], bpsi[p], alt, 'X', 20000)
         assert np.array_equal(np.isnan(a[p]), np.isnan(ref)) and rel_err(a[p], ref) < 1e-9
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_solo_kernel_matches_two_kernel_modes(vfo, golden, mode, monkeypatch):
+    """Single-profile calls run as ONE kernel (row setup + tile in the same CTA).  PRHF_NO_SOLO=1 forces the
+    planned two-kernel mode; both must agree with each other and with the goldens."""
+    from pyrayhf_b200 import _cabi
+    fx = golden.fixtures
+    for which in ("Day", "Night"):
+        args = (fx["freq_a"], fx[which + "_den"], fx[which + "_bmag"], fx[which + "_bpsi"], fx[which + "_alt"])
+        monkeypatch.delenv("PRHF_NO_SOLO", raising=False)
+        monkeypatch.setattr(_cabi, "_contexts", {})
+        a = vfo.vertical_forward_operator(*args, mode, 20000)
+        a2 = vfo.vertical_forward_operator(*args, mode, 20000)
+        assert np.array_equal(a, a2, equal_nan=True)
+        monkeypatch.setenv("PRHF_NO_SOLO", "1")
+        monkeypatch.setattr(_cabi, "_contexts", {})
+        b = vfo.vertical_forward_operator(*args, mode, 20000)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and rel_err(a, b) < 1e-12
+        tag = "%s_%s_20000_a" % (which, mode)
+        assert_parity(a, fx["ref_" + tag], fx["truth_" + tag], mode, "solo " + tag)
+    # failing profiles through the solo kernel
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    monkeypatch.delenv("PRHF_NO_SOLO", raising=False)
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    neg = den.copy()
+    neg[3] = -1.0
+    with pytest.raises(ValueError):
+        vfo.vertical_forward_operator(fx["freq_a"], neg, bmag, bpsi, alt, mode, 20000)
+    k = int(np.argmax(den))
+    with pytest.raises(IndexError):
+        vfo.vertical_forward_operator(fx["freq_a"], den[k:], bmag[k:], bpsi[k:], alt[k:], mode, 20000)
