@@ -551,6 +551,70 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     return;
   }
 
+  // ---- solo mode: the CTA owns ONE row, so all 256 threads share its scan ----
+  // Every thread screens its own levels (stride 256); the first level that may reach 1 (cand) comes from one
+  // block reduction; the thread owning cand and the threads owning the 255 levels below it evaluate theirs
+  // literally in lock-step (one sqrt/divide latency for the whole block); a second reduction yields the
+  // literal running max M below cand and the largest screen value further down, which must stay clearly
+  // below M.  Anything unusual (literal value at cand not above 1, a deep level competing with M, non-finite
+  // inputs) leaves solo_quick false and warp 0 runs the general scan below.
+  __shared__ int s_solo_quick, s_solo_cand;
+  __shared__ double s_solo_vc, s_solo_M;
+  if (p.k1_solo) {
+    if (tid == 0) s_solo_quick = 0;
+    const double f_hz0 = __dmul_rn(p.freq[prof * p.freq_stride + g], 1e6);
+    const double kx0 = (kCp * kCp) / __dmul_rn(f_hz0, f_hz0);
+    const double ky0 = (mode == 1) ? kGp / f_hz0 : 0.0;
+    const bool screen0 = status == 0 && !any_general && isfinite(kx0) && isfinite(ky0) && kx0 > 0.0;
+    if (screen0) {                                        // block-uniform
+      int my_cand = 0x7fffffff;
+      for (int k = tid; k < nt; k += kThreads) {
+        const double xk = s_den[k] * kx0, yk = s_b[k] * ky0;
+        if (my_cand == 0x7fffffff && xk + yk >= 1.0 - kScreenTol * (fabs(xk) + fabs(yk))) my_cand = k;
+      }
+      my_cand = warp_min_i(my_cand);
+      __syncthreads();
+      if (lane == 0) s_ri[wid] = my_cand;
+      __syncthreads();
+      int cand = s_ri[0];
+#pragma unroll
+      for (int k = 1; k < kThreads / 32; ++k) cand = min(cand, s_ri[k]);
+      if (cand == 0x7fffffff) {
+        if (tid == 0) { s_solo_cand = cand; s_solo_quick = 1; }   // no level can reach 1: no reflection
+      } else {
+        // own level inside the window (cand - 256, cand]
+        const int kw = cand - ((cand - tid) & (kThreads - 1));
+        double v = -CUDART_INF;
+        if (kw >= 0) {
+          v = x_literal(s_den[kw], f_hz0);
+          if (mode == 1) v = __dadd_rn(v, y_literal(s_b[kw], f_hz0));
+        }
+        // screen values (plus their error bound) of own levels below the window
+        double deep = -CUDART_INF;
+        for (int k = kw - kThreads; k >= 0; k -= kThreads) {
+          const double xk = s_den[k] * kx0, yk = s_b[k] * ky0;
+          deep = fmax(deep, xk + yk + kScreenTol * (fabs(xk) + fabs(yk)));
+        }
+        double below = (kw >= 0 && kw < cand) ? v : -CUDART_INF;
+        below = warp_max(below);
+        deep = warp_max(deep);
+        __syncthreads();
+        if (lane == 0) { s_ra[wid] = below; s_rb[wid] = deep; }
+        if (kw == cand) s_solo_vc = v;
+        __syncthreads();
+        if (tid == 0) {
+          double Mq = s_ra[0], dq = s_rb[0];
+#pragma unroll
+          for (int k = 1; k < kThreads / 32; ++k) { Mq = fmax(Mq, s_ra[k]); dq = fmax(dq, s_rb[k]); }
+          s_solo_cand = cand;
+          s_solo_M = Mq;
+          s_solo_quick = (s_solo_vc > 1.0 && (cand == 0 || dq < Mq)) ? 1 : 0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
   // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
   double* crit = s_crit + (size_t)wid * A;
   for (int rr = 0; rr < p.rows_per_warp; ++rr) {
@@ -577,7 +641,11 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     int jstar = 0x7fffffff;
     bool any_eq1 = false, has_nan = false;
     double v_jstar = 0.0, M = -CUDART_INF;
-    {
+    if (p.k1_solo && s_solo_quick) {
+      jstar = s_solo_cand;
+      v_jstar = s_solo_vc;
+      M = s_solo_M;
+    } else {
       const RowScan rs = row_scan_general(screen, mode, nt, lane, f_hz, kx, ky, s_den, s_b, crit);
       jstar = rs.jstar;
       v_jstar = rs.v_jstar;
