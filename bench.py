@@ -319,13 +319,15 @@ def run_b200_arm(args):
                        "l2": "flushed between timed steps (256 MiB write); every step timed with its own CUDA events"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic,
-                         "kernel": "prhf::vfo_tile_kernel<1,false>", "kernel_ms": kernel_ms,
+                         "kernel": ("prhf::vfo_solo_kernel<1,false> (row setup + grid points of a tile in one launch)"
+                                    if launches == args.steps else "prhf::vfo_tile_kernel<1,false>"),
+                         "kernel_ms": kernel_ms,
                          "rows_kernel_ms": rows_ms / max(pairs, 1),
                          "step_frac": (flops / (total_ms / args.steps * 1e-3) / 1e12) / peak_tf,
                          "algorithmic_flops_per_launch": flops,
                          "note": "achieved = W (77 flop per grid point of a reflecting row + 4 per profile level per row, "
-                                 "SURVEY 8d) / tile-kernel duration from CUDA events (prhf_kernel_timing); step_frac uses "
-                                 "the whole step (row-setup kernel + launch gaps included)",
+                                 "SURVEY 8d) / duration of the dominant kernel from CUDA events on its stream "
+                                 "(prhf_kernel_timing); step_frac uses the whole timed step",
                          "peak_source": "prhf_measure_fp64_peak: dependent-free DFMA kernel timed live on this GPU "
                                         "(MEASURED_PEAKS.json has no FP64 entry)",
                          "hbm_algorithmic_bytes_per_launch": hbm_bytes,
