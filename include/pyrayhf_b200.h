@@ -109,6 +109,53 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
                     void* cuda_stream);
 
 /*
+ * The individual stages of the path as standalone operators on DEVICE buffers (the fused operator above
+ * never materialises their arrays; these exist because the reference exposes every stage as a public
+ * function and its tutorial notebook plots the regridded arrays).  All asynchronous on cuda_stream.
+ *
+ * prhf_den2freq_f64   replaces den2freq, library.py:75-97: freq_out[i] = sqrt(density[i]) * 8.97866275.
+ *                     *negative_flag (device int, may be NULL; caller zeroes it) is OR-ed with 1 if any
+ *                     density < 0 -- the reference raises ValueError("Density must be non-negative") there.
+ * prhf_find_x_f64     replaces find_X, library.py:120-137: X = den2freq(n_e)**2 / f**2 in that rounding order.
+ *                     Strides are 0 (scalar operand) or 1.
+ * prhf_find_y_f64     replaces find_Y, library.py:140-158: Y = g_p * b / f.
+ * prhf_smooth_grid_f64 replaces smooth_nonuniform_grid(start, end, n_points, sharpness), library.py:296-321.
+ */
+int prhf_den2freq_f64(prhf_ctx* ctx, const double* density, int64_t n, double* freq_out, int* negative_flag,
+                      void* cuda_stream);
+int prhf_find_x_f64(prhf_ctx* ctx, const double* n_e, int64_t n_e_stride, const double* f_hz, int64_t f_stride,
+                    int64_t n, double* x_out, int* negative_flag, void* cuda_stream);
+int prhf_find_y_f64(prhf_ctx* ctx, const double* f_hz, int64_t f_stride, const double* b, int64_t b_stride, int64_t n,
+                    double* y_out, void* cuda_stream);
+int prhf_smooth_grid_f64(prhf_ctx* ctx, double start, double end, int n_points, double sharpness, double* x_out,
+                         void* cuda_stream);
+
+/*
+ * Replaces regrid_to_nonuniform_grid, library.py:324-438, for ONE profile: truncation below the density peak,
+ * critical curve, reflection heights, stretched altitudes and the profile sampled on them.
+ *   f_hz [n_freq] in Hz (this stage of the reference takes Hz, library.py:333-334); n_e, b, bpsi, aalt [n_alt]
+ *   crit_height [n_freq]: h_c (library.py:407), NaN where the frequency never reflects (required)
+ *   alt_out, dist_out, den_out, bmag_out, bpsi_out [n_freq x n_points] row-major: the 'alt', 'dist', 'den',
+ *   'bmag', 'bpsi' entries of the reference's dict (library.py:430-438); any of them may be NULL.
+ *   status [1] device int (may be NULL): 0 ok, 1 negative density below the peak (library.py:94),
+ *   2 density peak at index 0 (library.py:399).  The 'freq', 'crit_height' and 'ind' entries are broadcasts
+ *   the host builds.
+ */
+int prhf_regrid_f64(prhf_ctx* ctx, const double* f_hz, int n_freq, const double* n_e, const double* b,
+                    const double* bpsi, const double* aalt, int n_alt, int mode, int n_points, double* crit_height,
+                    double* alt_out, double* dist_out, double* den_out, double* bmag_out, double* bpsi_out, int* status,
+                    void* cuda_stream);
+
+/*
+ * Replaces find_vh, library.py:259-293: mu' from (X, Y, bpsi) [n_rows x n_cols], vh[r] = nansum(mu' * dh) with
+ * 0 -> NaN, + alt_min.  The unmagnetised switch (library.py:201, nanmax|Y| < 1e-12 over the WHOLE array) is
+ * evaluated on the device.
+ */
+int prhf_find_vh_f64(prhf_ctx* ctx, const double* X, const double* Y, const double* bpsi_deg, const double* dh,
+                     int64_t n_rows, int64_t n_cols, double alt_min, int mode, unsigned flags, double* vh_out,
+                     void* cuda_stream);
+
+/*
  * Residual of the inversion objective on DEVICE buffers (replaces the arithmetic tail of residual_VH,
  * library.py:660-668, for a batch of candidate profiles): NaN model heights are replaced by
  * max(nanmean|vh_model[p,:]|, 100) (library.py:664-665), residual = vh_obs - vh_model (library.py:668).

@@ -43,6 +43,20 @@ def stretch_multiplier(n_points, sharpness=SHARPNESS):
     return 1.0 - (0.0 + (1.0 - 0.0) * factor)
 
 
+def smooth_grid(start, end, n_points, sharpness):
+    """General stretched grid.  library.py:296-321."""
+    u = np.linspace(0.0, 1.0, n_points)
+    factor = (np.exp(sharpness * (1.0 - u)) - 1.0) / (np.exp(sharpness) - 1.0)
+    return 1. - (start + (end - start) * factor)
+
+
+def den2freq(den):
+    """sqrt(density) * cp with the negative-density check.  library.py:75-97."""
+    if np.any(np.asarray(den) < 0):
+        raise ValueError("Density must be non-negative")
+    return np.sqrt(den) * CP_HZ_PER_SQRT_M3
+
+
 def plasma_ratio_x(den, f_hz):
     """X = (sqrt(n) * cp)**2 / f**2 with the reference's rounding order.
 
@@ -105,6 +119,24 @@ def regrid(f_hz, den, bmag, bpsi, alt, mode, n_points):
     for key, tab in (('den', den_t), ('bmag', bmag_t), ('bpsi', bpsi_t)):
         out[key] = np.interp(flat, alt_t, tab).reshape(h.shape)     # library.py:424-426
     return out
+
+
+def regrid_dict(f_hz, den, bmag, bpsi, alt, mode, n_points):
+    """The reference's regridded dict (same keys and shapes).  library.py:418-438."""
+    g = regrid(f_hz, den, bmag, bpsi, alt, mode, n_points)
+    n_freq = f_hz.size
+    return {'freq': np.transpose(np.full((n_points, n_freq), f_hz)),
+            'den': g['den'], 'bmag': g['bmag'], 'bpsi': g['bpsi'], 'dist': g['dh'], 'alt': g['h'],
+            'crit_height': np.transpose(np.broadcast_to(g['h_c'], (n_points, n_freq))),
+            'ind': np.full((n_freq, n_points), np.arange(0, n_points, 1))}
+
+
+def find_vh_rows(x, y, psi_deg, dh, alt_min, mode):
+    """Row sums of mu' * dh.  library.py:259-293."""
+    _, mup = appleton_hartree(x, y, psi_deg, mode)
+    s = np.nansum(mup * dh, axis=1)
+    s[s == 0] = np.nan
+    return s + alt_min
 
 
 def appleton_hartree(x, y, psi_deg, mode):

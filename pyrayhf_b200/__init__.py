@@ -22,3 +22,13 @@ from pyrayhf_b200.library import (  # noqa: E402,F401
     install,
     uninstall,
 )
+from pyrayhf_b200 import stages  # noqa: E402,F401
+from pyrayhf_b200.stages import (  # noqa: E402,F401
+    constants,
+    den2freq,
+    find_X,
+    find_Y,
+    smooth_nonuniform_grid,
+    regrid_to_nonuniform_grid,
+    find_vh,
+)

@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = (
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
     "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
     "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64",
+    "prhf_den2freq_f64", "prhf_find_x_f64", "prhf_find_y_f64", "prhf_smooth_grid_f64",
+    "prhf_regrid_f64", "prhf_find_vh_f64",
 )
 
 _vp = ctypes.c_void_p
@@ -91,6 +93,20 @@ def load():
         L.prhf_kernel_timing.restype = _i
         L.prhf_residual_f64.argtypes = [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]
         L.prhf_residual_f64.restype = _i
+        _d = ctypes.c_double
+        L.prhf_den2freq_f64.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp]
+        L.prhf_den2freq_f64.restype = _i
+        L.prhf_find_x_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp]
+        L.prhf_find_x_f64.restype = _i
+        L.prhf_find_y_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]
+        L.prhf_find_y_f64.restype = _i
+        L.prhf_smooth_grid_f64.argtypes = [_vp, _d, _d, _i, _d, _vp, _vp]
+        L.prhf_smooth_grid_f64.restype = _i
+        L.prhf_regrid_f64.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp]
+        L.prhf_regrid_f64.restype = _i
+        L.prhf_find_vh_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _d, _i, _u, _vp, _vp]
+        L.prhf_find_vh_f64.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L

@@ -53,7 +53,8 @@ struct prhf_ctx {
   long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
   size_t trace_k1_off = 0;           // K1 entries start here (in long longs)
   // planned mode (small batches): tile plan, compact tile list, K1 completion counter
-  unsigned* live_count = nullptr;    // [0] live-row counter of planned mode, [2..3] the fused kernel's barrier words
+  unsigned* live_count = nullptr;    // [0] live-row counter of planned mode, [2..3] the fused kernel's barrier words,
+                                     // [4..5] 8-byte scratch word of prhf_find_vh_f64
   bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
   bool use_solo = true;              // PRHF_NO_SOLO=1: single-profile calls through the two-kernel planned mode
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
@@ -144,8 +145,8 @@ int ensure_records(prhf_ctx* ctx, size_t n_prof, size_t n_rows) {
 
 int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
   if (!ctx->live_count) {
-    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_count, 4 * sizeof(unsigned)));
-    PRHF_CUDA(ctx, cudaMemset(ctx->live_count, 0, 4 * sizeof(unsigned)));
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_count, 8 * sizeof(unsigned)));
+    PRHF_CUDA(ctx, cudaMemset(ctx->live_count, 0, 8 * sizeof(unsigned)));
   }
   if (n_rows > ctx->live_list_cap) {
     if (ctx->live_list) cudaFree(ctx->live_list);
@@ -490,6 +491,8 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
     P.n_cand = n_cand;
     for (int c = 0; c < prhf::kMaxPlanCand; ++c) { P.cand_seg[c] = cand_seg[c]; P.cand_len[c] = cand_len[c]; }
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
+    P.freq_scale = 1e6;                                       // lib:491
+    P.row_hc = nullptr;
     if (solo) {
       if (ctx->kernel_timing) PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
       PRHF_CUDA(ctx, prhf::launch_vfo_solo(P, mode, literal, np * tiles_per_profile, stream));
@@ -701,6 +704,134 @@ int prhf_mu_mup_f64(prhf_ctx* ctx, const double* X, const double* Y, const doubl
   PRHF_CUDA(ctx, prhf::launch_mu_mup(X, Y, bpsi_deg, n, mode, isotropic != 0, (flags & PRHF_FLAG_LITERAL) != 0, mu_out,
                                      mup_out, (cudaStream_t)cuda_stream));
   ctx->launches++;
+  return PRHF_OK;
+}
+
+// ---- standalone stages (vfo_stages.cu); device pointers, asynchronous on the stream ----
+int prhf_den2freq_f64(prhf_ctx* ctx, const double* density, int64_t n, double* freq_out, int* negative_flag,
+                      void* cuda_stream) {
+  if (!ctx || n < 0) return PRHF_ERR_INVALID_ARG;
+  if (n == 0) return PRHF_OK;
+  if (!density || !freq_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_den2freq(density, n, freq_out, negative_flag, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_find_x_f64(prhf_ctx* ctx, const double* n_e, int64_t n_e_stride, const double* f_hz, int64_t f_stride,
+                    int64_t n, double* x_out, int* negative_flag, void* cuda_stream) {
+  if (!ctx || n < 0 || (n_e_stride != 0 && n_e_stride != 1) || (f_stride != 0 && f_stride != 1))
+    return PRHF_ERR_INVALID_ARG;
+  if (n == 0) return PRHF_OK;
+  if (!n_e || !f_hz || !x_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_find_x(n_e, n_e_stride, f_hz, f_stride, n, x_out, negative_flag,
+                                     (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_find_y_f64(prhf_ctx* ctx, const double* f_hz, int64_t f_stride, const double* b, int64_t b_stride, int64_t n,
+                    double* y_out, void* cuda_stream) {
+  if (!ctx || n < 0 || (b_stride != 0 && b_stride != 1) || (f_stride != 0 && f_stride != 1))
+    return PRHF_ERR_INVALID_ARG;
+  if (n == 0) return PRHF_OK;
+  if (!f_hz || !b || !y_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_find_y(f_hz, f_stride, b, b_stride, n, y_out, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_smooth_grid_f64(prhf_ctx* ctx, double start, double end, int n_points, double sharpness, double* x_out,
+                         void* cuda_stream) {
+  if (!ctx || n_points < 0) return PRHF_ERR_INVALID_ARG;
+  if (n_points == 0) return PRHF_OK;
+  if (!x_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_smooth_grid(start, end, n_points, sharpness, x_out, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_regrid_f64(prhf_ctx* ctx, const double* f_hz, int n_freq, const double* n_e, const double* b,
+                    const double* bpsi, const double* aalt, int n_alt, int mode, int n_points, double* crit_height,
+                    double* alt_out, double* dist_out, double* den_out, double* bmag_out, double* bpsi_out, int* status,
+                    void* cuda_stream) {
+  int rc = validate(ctx, f_hz, n_freq, n_e, b, bpsi, aalt, 1, n_alt, mode, n_points, crit_height);
+  if (rc != PRHF_OK) return rc;
+  if (n_freq == 0) return PRHF_OK;
+  if (n_freq > 65535) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  const double* mult = nullptr;
+  rc = get_multiplier(ctx, n_points, stream, &mult);
+  if (rc != PRHF_OK) return rc;
+  rc = ensure_records(ctx, 1, (size_t)2 * n_freq);            // row spans + a scratch row for the setup kernel's vh
+  if (rc != PRHF_OK) return rc;
+  prhf::VfoParams P{};
+  P.freq = f_hz;
+  P.freq_scale = 1.0;                                         // this stage takes Hz (lib:333-334)
+  P.n_freq = n_freq;
+  P.den = n_e;
+  P.bmag = b;
+  P.bpsi = bpsi;
+  P.alt = aalt;
+  P.n_alt = n_alt;
+  P.mult = mult;
+  P.n_points = n_points;
+  P.seg_len = n_points;
+  P.n_seg = 1;
+  P.rows_per_warp = 1;
+  P.vh = ctx->row_span + n_freq;
+  P.status = status;
+  P.prof_rec = ctx->prof_rec;
+  P.row_span = ctx->row_span;
+  P.row_hc = crit_height;
+  P.rows_in_launch = n_freq;
+  P.max_seg = 1;
+  P.n_sm = ctx->sm_count;
+  PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, 1, stream));
+  prhf::RegridParams R;
+  R.f_hz = f_hz;
+  R.n_freq = n_freq;
+  R.den = n_e;
+  R.bmag = b;
+  R.bpsi = bpsi;
+  R.alt = aalt;
+  R.rec = ctx->prof_rec;
+  R.row_hc = crit_height;
+  R.mult = mult;
+  R.n_points = n_points;
+  R.alt_out = alt_out;
+  R.dist_out = dist_out;
+  R.den_out = den_out;
+  R.bmag_out = bmag_out;
+  R.bpsi_out = bpsi_out;
+  ctx->launches++;
+  if (alt_out || dist_out || den_out || bmag_out || bpsi_out) {
+    PRHF_CUDA(ctx, prhf::launch_regrid_write(R, n_alt, stream));
+    ctx->launches++;
+  }
+  return PRHF_OK;
+}
+
+int prhf_find_vh_f64(prhf_ctx* ctx, const double* X, const double* Y, const double* bpsi_deg, const double* dh,
+                     int64_t n_rows, int64_t n_cols, double alt_min, int mode, unsigned flags, double* vh_out,
+                     void* cuda_stream) {
+  if (!ctx || n_rows < 0 || n_cols < 0) return PRHF_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return PRHF_ERR_BAD_MODE;
+  if (n_rows == 0) return PRHF_OK;
+  if (!vh_out || (n_cols > 0 && (!X || !Y || !bpsi_deg || !dh))) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  int rc = ensure_plan(ctx, 1);                               // allocates the scratch word
+  if (rc != PRHF_OK) return rc;
+  PRHF_CUDA(ctx, prhf::launch_find_vh(X, Y, bpsi_deg, dh, n_rows, n_cols, alt_min, mode,
+                                      (flags & PRHF_FLAG_LITERAL) != 0,
+                                      reinterpret_cast<unsigned long long*>(ctx->live_count + 4), vh_out,
+                                      (cudaStream_t)cuda_stream));
+  ctx->launches += 2;
   return PRHF_OK;
 }
 

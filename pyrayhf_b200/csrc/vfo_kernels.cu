@@ -426,7 +426,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   if (status == 0 && bmax < 1e-9) {
     double fmin_abs = CUDART_INF;
     for (int k = tid; k < p.n_freq; k += kThreads) {
-      const double f = fabs(__dmul_rn(p.freq[prof * p.freq_stride + k], 1e6));
+      const double f = fabs(__dmul_rn(p.freq[prof * p.freq_stride + k], p.freq_scale));
       if (f > 0.0) fmin_abs = fmin(fmin_abs, f);
     }
     fmin_abs = block_min(fmin_abs, sc);
@@ -466,9 +466,10 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     if (status != 0) {
       p.vh[out_idx] = CUDART_NAN;
       p.row_span[lrow] = CUDART_NAN;
+      if (p.row_hc) p.row_hc[lrow] = CUDART_NAN;
       return;
     }
-    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], p.freq_scale);   // lib:491
     const double kx = (kCp * kCp) / __dmul_rn(f_hz, f_hz);
     const double ky = (mode == 1) ? kGp / f_hz : 0.0;
     bool slow = any_general || !(isfinite(kx) && isfinite(ky) && kx > 0.0);
@@ -531,6 +532,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
                                    : CUDART_NAN;
       p.vh[out_idx] = res;
       p.row_span[lrow] = CUDART_NAN;
+      if (p.row_hc) p.row_hc[lrow] = CUDART_NAN;
       return;
     }
     double hcrit;
@@ -548,6 +550,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       }
     }
     p.row_span[lrow] = __dsub_rn(__dsub_rn(hcrit, kBackoff), s_alt[0]);   // lib:407, lib:413
+    if (p.row_hc) p.row_hc[lrow] = __dsub_rn(hcrit, kBackoff);
     return;
   }
 
@@ -562,7 +565,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   __shared__ double s_solo_vc, s_solo_M;
   if (p.k1_solo) {
     if (tid == 0) s_solo_quick = 0;
-    const double f_hz0 = __dmul_rn(p.freq[prof * p.freq_stride + g], 1e6);
+    const double f_hz0 = __dmul_rn(p.freq[prof * p.freq_stride + g], p.freq_scale);
     const double kx0 = (kCp * kCp) / __dmul_rn(f_hz0, f_hz0);
     const double ky0 = (mode == 1) ? kGp / f_hz0 : 0.0;
     const bool screen0 = status == 0 && !any_general && isfinite(kx0) && isfinite(ky0) && kx0 > 0.0;
@@ -623,10 +626,14 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     const int64_t out_idx = prof * p.n_freq + r;
     const int64_t lrow = lprof * p.n_freq + r;
     if (status != 0) {
-      if (lane == 0) { p.vh[out_idx] = CUDART_NAN; p.row_span[lrow] = CUDART_NAN; }
+      if (lane == 0) {
+        p.vh[out_idx] = CUDART_NAN;
+        p.row_span[lrow] = CUDART_NAN;
+        if (p.row_hc) p.row_hc[lrow] = CUDART_NAN;
+      }
       continue;
     }
-    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);   // lib:491
+    const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], p.freq_scale);   // lib:491
 
     // Critical curve at the nodes (lib:380-399): v_k = X_k (O) or X_k + Y_k (X) in the reference's rounding
     // order.  The reference needs: does any v_k reach 1 (validity), the first k with v_k > 1 (jstar), the
@@ -659,6 +666,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
         p.vh[out_idx] = (nt == 1) ? dead_row_single_level(mode, iso, s_den[0], s_b[0], s_psi[0], f_hz, alt_min)
                                   : CUDART_NAN;
         p.row_span[lrow] = CUDART_NAN;
+        if (p.row_hc) p.row_hc[lrow] = CUDART_NAN;
       }
       __syncwarp();
       continue;
@@ -682,6 +690,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
       const double span = __dsub_rn(hc, s_alt[0]);          // lib:413 (h_c - aalt[0])
       p.row_span[lrow] = span;
+      if (p.row_hc) p.row_hc[lrow] = hc;
       if (s_span) *s_span = span;
       if (p.live_count) {                                   // planned mode: compact list of rows that reflect
         LiveRow e;

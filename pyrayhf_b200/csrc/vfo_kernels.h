@@ -87,6 +87,9 @@ struct VfoParams {
   int cand_seg[kMaxPlanCand];
   int cand_len[kMaxPlanCand];
   long long* trace_k1;     // developer phase trace of K1 [ctas x 8] (PRHF_TRACE builds), else null
+  double freq_scale;       // row setup: f_hz = freq * freq_scale (1e6 for MHz input, lib:491; 1 for the Hz input of
+                           // the standalone regrid stage).  The tile kernels always assume MHz.
+  double* row_hc;          // optional [rows_in_launch]: reflection height h_c (lib:407), NaN on rows without one
 };
 
 size_t vfo_smem_bytes(int n_alt);
@@ -102,6 +105,27 @@ cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, i
                           bool literal, double* mu, double* mup, cudaStream_t stream);
 cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
                             double* chi2, cudaStream_t stream);
+// standalone stages (vfo_stages.cu)
+cudaError_t launch_den2freq(const double* den, int64_t n, double* out, int* negative_flag, cudaStream_t stream);
+cudaError_t launch_find_x(const double* den, int64_t den_stride, const double* f_hz, int64_t f_stride, int64_t n,
+                          double* X, int* negative_flag, cudaStream_t stream);
+cudaError_t launch_find_y(const double* f_hz, int64_t f_stride, const double* b, int64_t b_stride, int64_t n, double* Y,
+                          cudaStream_t stream);
+cudaError_t launch_smooth_grid(double start, double end, int n_points, double sharpness, double* x, cudaStream_t stream);
+struct RegridParams {
+  const double* f_hz;      // [n_freq]
+  int n_freq;
+  const double *den, *bmag, *bpsi, *alt;   // one profile, [n_alt]
+  const ProfileRecord* rec;                // from the row-setup kernel (truncation index)
+  const double* row_hc;    // [n_freq]
+  const double* mult;      // [n_points + kMultPad]
+  int n_points;
+  double *alt_out, *dist_out, *den_out, *bmag_out, *bpsi_out;   // [n_freq x n_points], any may be null
+};
+cudaError_t launch_regrid_write(const RegridParams& p, int n_alt, cudaStream_t stream);
+cudaError_t launch_find_vh(const double* X, const double* Y, const double* psi, const double* dh, int64_t n_rows,
+                           int64_t n_cols, double alt_min, int mode, bool literal, unsigned long long* scratch_word,
+                           double* vh, cudaStream_t stream);
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_math_selftest(int n, double* err2, cudaStream_t stream);
 

@@ -278,20 +278,31 @@ def brute_force_fit(freq, vh_obs, den_candidates, bmag, bpsi, alt, mode='O', n_p
 _saved = {}
 
 
-def install():
+_STAGE_NAMES = ('den2freq', 'find_X', 'find_Y', 'smooth_nonuniform_grid', 'regrid_to_nonuniform_grid',
+                'find_mu_mup', 'find_vh')
+
+
+def install(stages=False):
     """Rebind ``PyRayHF.library.vertical_forward_operator`` to this implementation.
 
     ``model_VH`` resolves the name through its module globals at call time
     (library.py:589), so the inversion code picks the GPU path up unchanged.
+    ``stages=True`` also rebinds the standalone stage functions (pyrayhf_b200/stages.py); leave it off
+    when the reference's ray tracers are in use -- they call ``find_X`` / ``find_mu_mup`` on a handful of
+    values per step, where a GPU round trip per call is slower than numpy.
     """
     import PyRayHF.library as ref
-    if 'vertical_forward_operator' not in _saved:
-        _saved['vertical_forward_operator'] = ref.vertical_forward_operator
-    ref.vertical_forward_operator = vertical_forward_operator
+    names = ('vertical_forward_operator',) + (_STAGE_NAMES if stages else ())
+    import pyrayhf_b200
+    for name in names:
+        if name not in _saved:
+            _saved[name] = getattr(ref, name)
+        setattr(ref, name, getattr(pyrayhf_b200, name))
     return ref
 
 
 def uninstall():
-    if 'vertical_forward_operator' in _saved:
+    if _saved:
         import PyRayHF.library as ref
-        ref.vertical_forward_operator = _saved.pop('vertical_forward_operator')
+        for name in list(_saved):
+            setattr(ref, name, _saved.pop(name))
