@@ -156,6 +156,15 @@ int prhf_find_vh_f64(prhf_ctx* ctx, const double* X, const double* Y, const doub
                      void* cuda_stream);
 
 /*
+ * Synthetic inputs on the DEVICE: two Chapman layers + centred axial dipole (the benchmark generator of
+ * pyrayhf_b200/synth.py; stands in for generate_input_1D / calculate_magnetic_field, library.py:2390-2694, whose
+ * PyIRI / IGRF dependencies are not available offline).  params [n_profiles x 5] = {foF2 MHz, hmF2 km, scale
+ * height km, foE MHz, latitude deg}; alt [n_alt]; den_out, bmag_out, bpsi_out [n_profiles x n_alt].
+ */
+int prhf_synth_profiles_f64(prhf_ctx* ctx, const double* params, int64_t n_profiles, const double* alt, int n_alt,
+                            double* den_out, double* bmag_out, double* bpsi_out, void* cuda_stream);
+
+/*
  * Residual of the inversion objective on DEVICE buffers (replaces the arithmetic tail of residual_VH,
  * library.py:660-668, for a batch of candidate profiles): NaN model heights are replaced by
  * max(nanmean|vh_model[p,:]|, 100) (library.py:664-665), residual = vh_obs - vh_model (library.py:668).

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
     "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64",
     "prhf_den2freq_f64", "prhf_find_x_f64", "prhf_find_y_f64", "prhf_smooth_grid_f64",
-    "prhf_regrid_f64", "prhf_find_vh_f64",
+    "prhf_regrid_f64", "prhf_find_vh_f64", "prhf_synth_profiles_f64",
 )
 
 _vp = ctypes.c_void_p
@@ -107,6 +107,8 @@ def load():
         L.prhf_regrid_f64.restype = _i
         L.prhf_find_vh_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _d, _i, _u, _vp, _vp]
         L.prhf_find_vh_f64.restype = _i
+        L.prhf_synth_profiles_f64.argtypes = [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp]
+        L.prhf_synth_profiles_f64.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L

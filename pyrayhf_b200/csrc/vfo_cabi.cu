@@ -835,6 +835,18 @@ int prhf_find_vh_f64(prhf_ctx* ctx, const double* X, const double* Y, const doub
   return PRHF_OK;
 }
 
+int prhf_synth_profiles_f64(prhf_ctx* ctx, const double* params, int64_t n_profiles, const double* alt, int n_alt,
+                            double* den_out, double* bmag_out, double* bpsi_out, void* cuda_stream) {
+  if (!ctx || n_profiles < 0 || n_alt < 0) return PRHF_ERR_INVALID_ARG;
+  if (n_profiles == 0 || n_alt == 0) return PRHF_OK;
+  if (!params || !alt || !den_out || !bmag_out || !bpsi_out) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_synth_profiles(params, n_profiles, alt, n_alt, den_out, bmag_out, bpsi_out,
+                                             (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
 int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_obs, int64_t n_profiles, int n_freq,
                       double* residual_out, double* chi2_out, void* cuda_stream) {
   if (!ctx || n_profiles < 0 || n_freq < 0) return PRHF_ERR_INVALID_ARG;

@@ -126,6 +126,8 @@ cudaError_t launch_regrid_write(const RegridParams& p, int n_alt, cudaStream_t s
 cudaError_t launch_find_vh(const double* X, const double* Y, const double* psi, const double* dh, int64_t n_rows,
                            int64_t n_cols, double alt_min, int mode, bool literal, unsigned long long* scratch_word,
                            double* vh, cudaStream_t stream);
+cudaError_t launch_synth_profiles(const double* params, int64_t n_profiles, const double* alt, int n_alt, double* den,
+                                  double* bmag, double* bpsi, cudaStream_t stream);
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_math_selftest(int n, double* err2, cudaStream_t stream);
 

@@ -204,6 +204,39 @@ __global__ void __launch_bounds__(kStageThreads) find_vh_kernel(const double* __
   }
 }
 
+// ---- synthetic inputs on the device (SURVEY 8d "Common inputs"; pyrayhf_b200/synth.py is the host form) ----
+// Two Chapman layers + centred axial dipole.  params[p] = {foF2 MHz, hmF2 km, H km, foE MHz, latitude deg}.
+// One CTA per profile; replaces the PyIRI / IGRF input builders of lib:2390-2694, which are not available offline.
+__device__ __forceinline__ double chapman_layer(double alt, double nm, double hm, double scale_h) {
+  const double z = (alt - hm) / scale_h;
+  return nm * exp(0.5 * (1.0 - z - exp(-z)));
+}
+__global__ void __launch_bounds__(kStageThreads) synth_profiles_kernel(const double* __restrict__ params, int64_t n_profiles,
+                                                                       const double* __restrict__ alt, int n_alt,
+                                                                       double* __restrict__ den, double* __restrict__ bmag,
+                                                                       double* __restrict__ bpsi) {
+  constexpr double kB0 = 3.12e-5, kRe = 6371.0;
+  for (int64_t pr = blockIdx.x; pr < n_profiles; pr += gridDim.x) {
+    const double* q = params + pr * 5;
+    const double f2 = q[0] * 1e6 / kCp, fe = q[3] * 1e6 / kCp;
+    const double nmf2 = f2 * f2, nme = fe * fe, hm = q[1], sh = q[2];
+    const double lat = q[4] * kDeg2Rad;
+    double sl, cl;
+    sincos(lat, &sl, &cl);
+    const double lat_factor = sqrt(1.0 + 3.0 * sl * sl);
+    const double incl = atan2(2.0 * sl, cl) * (180.0 / CUDART_PI);
+    const double psi = 90.0 - fabs(incl);
+    for (int k = threadIdx.x; k < n_alt; k += blockDim.x) {
+      const double a = alt[k];
+      const int64_t o = pr * n_alt + k;
+      den[o] = chapman_layer(a, nmf2, hm, sh) + chapman_layer(a, nme, 110.0, 8.0);
+      const double r = kRe / (kRe + a);
+      bmag[o] = kB0 * (r * r * r) * lat_factor;
+      bpsi[o] = psi;
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_den2freq(const double* den, int64_t n, double* out, int* negative_flag, cudaStream_t stream) {
@@ -268,6 +301,15 @@ cudaError_t launch_find_vh(const double* X, const double* Y, const double* psi, 
   else if (literal) PRHF_LAUNCH(1, true);
   else PRHF_LAUNCH(1, false);
 #undef PRHF_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_profiles(const double* params, int64_t n_profiles, const double* alt, int n_alt, double* den,
+                                  double* bmag, double* bpsi, cudaStream_t stream) {
+  if (n_profiles <= 0 || n_alt <= 0) return cudaSuccess;
+  int64_t ctas = n_profiles;
+  if (ctas > 148 * 64) ctas = 148 * 64;
+  synth_profiles_kernel<<<(unsigned)ctas, kStageThreads, 0, stream>>>(params, n_profiles, alt, n_alt, den, bmag, bpsi);
   return cudaGetLastError();
 }
 

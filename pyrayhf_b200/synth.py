@@ -58,6 +58,36 @@ def profiles_from_parameters(fof2, hmf2, scale_h, foe, lat_deg, alt=None):
     return den, np.ascontiguousarray(bmag), bpsi
 
 
+def profiles_from_parameters_device(fof2, hmf2, scale_h, foe, lat_deg, alt=None, device=None):
+    """``profiles_from_parameters`` evaluated by the CUDA generator kernel: float64 CUDA tensors
+    ``(den, bmag, bpsi)`` of shape ``[P, A]`` that never touch the host (config 4 builds its 8 192-profile
+    chunks this way, so the ensemble needs no host-to-device traffic beyond 40 bytes per profile)."""
+    import ctypes
+    import torch
+    from pyrayhf_b200 import _cabi
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    alt = default_alt() if alt is None else np.asarray(alt, dtype=float)
+    cols = [np.atleast_1d(np.asarray(v, dtype=float)) for v in (fof2, hmf2, scale_h, foe, lat_deg)]
+    params = torch.from_numpy(np.ascontiguousarray(np.stack(np.broadcast_arrays(*cols), axis=1))).to(dev)
+    t_alt = torch.from_numpy(np.ascontiguousarray(alt)).to(dev)
+    n_prof, n_alt = params.shape[0], t_alt.numel()
+    den, bmag, bpsi = (torch.empty((n_prof, n_alt), dtype=torch.float64, device=dev) for _ in range(3))
+    ctx = _cabi.context(dev.index)
+    vp = ctypes.c_void_p
+    ctx.check(ctx.lib.prhf_synth_profiles_f64(ctx.handle, vp(params.data_ptr()), n_prof, vp(t_alt.data_ptr()), n_alt,
+                                              vp(den.data_ptr()), vp(bmag.data_ptr()), vp(bpsi.data_ptr()),
+                                              vp(torch.cuda.current_stream(dev).cuda_stream)))
+    return den, bmag, bpsi
+
+
+def ensemble_member_parameters(lat_deg, lon_deg, member):
+    """Layer parameters of one config-4 ensemble member (the perturbation of ``ensemble_member``)."""
+    lat_deg = np.atleast_1d(np.asarray(lat_deg, dtype=float))
+    fof2, hmf2, scale_h, foe = layer_parameters(lat_deg, lon_deg)
+    xi = np.random.default_rng(1000 + int(member)).standard_normal((3, lat_deg.size))
+    return fof2 * np.exp(0.05 * xi[0]), hmf2 + 10.0 * xi[1], scale_h * np.exp(0.05 * xi[2]), foe, lat_deg
+
+
 def profiles_at(lat_deg, lon_deg, alt=None):
     """[P, A] den / bmag / bpsi for geographic points (1-D arrays of length P)."""
     lat_deg = np.atleast_1d(np.asarray(lat_deg, dtype=float))
@@ -89,12 +119,8 @@ def grid_subset(n_profiles, seed=20260101):
 
 def ensemble_member(lat_deg, lon_deg, member, alt=None):
     """Config 4: perturbed copy of the base profiles for one ensemble member."""
-    lat_deg = np.atleast_1d(np.asarray(lat_deg, dtype=float))
-    fof2, hmf2, scale_h, foe = layer_parameters(lat_deg, lon_deg)
-    xi = np.random.default_rng(1000 + int(member)).standard_normal((3, lat_deg.size))
     # NmF2 * exp(0.10 xi1)  <=>  foF2 * exp(0.05 xi1)
-    return profiles_from_parameters(fof2 * np.exp(0.05 * xi[0]), hmf2 + 10.0 * xi[1],
-                                    scale_h * np.exp(0.05 * xi[2]), foe, lat_deg, alt)
+    return profiles_from_parameters(*ensemble_member_parameters(lat_deg, lon_deg, member), alt)
 
 
 def bench_day_profile(alt=None, rank=0):

@@ -190,3 +190,26 @@ def test_find_vh_mode_and_iso_switch(st):
         got = st.find_vh(Xl, Yl, pl, dl, 90.0, mode)
         ref = vfo_oracle.find_vh_rows(Xl, Yl, pl, dl, 90.0, mode)
         assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.allclose(got, ref, rtol=1e-9, equal_nan=True)
+
+
+def test_device_profile_generator_matches_host_generator():
+    import torch
+    import pyrayhf_b200
+    lat, lon = synth.grid_subset(300)
+    par = synth.ensemble_member_parameters(lat, lon, member=7)
+    den_h, bmag_h, bpsi_h = synth.profiles_from_parameters(*par)
+    den_d, bmag_d, bpsi_d = synth.profiles_from_parameters_device(*par)
+    assert den_d.is_cuda and den_d.shape == den_h.shape
+    close(den_d.cpu().numpy(), den_h, rtol=1e-11)
+    close(bmag_d.cpu().numpy(), bmag_h, rtol=1e-13)
+    close(bpsi_d.cpu().numpy(), bpsi_h, rtol=1e-12, atol=1e-12)
+    # the forward operator on the device-built batch == on the host-built batch (no host copy of the profiles)
+    dev = den_d.device
+    freq = torch.from_numpy(synth.default_freq()).to(dev)
+    alt = torch.from_numpy(synth.default_alt()).to(dev)
+    vh_d = pyrayhf_b200.vertical_forward_operator_batched(freq, den_d, bmag_d, bpsi_d, alt, 'X', 2000).cpu().numpy()
+    vh_h = pyrayhf_b200.vertical_forward_operator_batched(synth.default_freq(), den_h, bmag_h, bpsi_h,
+                                                          synth.default_alt(), 'X', 2000)
+    assert np.array_equal(np.isnan(vh_d), np.isnan(vh_h))
+    m = np.isfinite(vh_h)
+    assert np.allclose(vh_d[m], vh_h[m], rtol=1e-8, atol=0)     # inputs differ by ~1e-13; rows near cutoff amplify that
