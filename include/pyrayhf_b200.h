@@ -165,6 +165,24 @@ int prhf_synth_profiles_f64(prhf_ctx* ctx, const double* params, int64_t n_profi
                             double* den_out, double* bmag_out, double* bpsi_out, void* cuda_stream);
 
 /*
+ * Stratified Snell's-law ray tracers on DEVICE buffers, batched over rays (replace trace_ray_cartesian_snells,
+ * library.py:1096-1268 with its helpers library.py:1034-1093, and trace_ray_spherical_snells,
+ * library.py:1460-1713; the reference traces one ray per call).  Ray i has frequency f0_hz[i] (Hz) and launch
+ * elevation elevation_deg[i]; all rays share the profile alt_km, ne, babs, bpsi [n_alt].
+ *   geometry 0 = flat Earth, 1 = spherical Earth (dz_target_km, apex_boost, max_substeps, r_e_km as the
+ *   reference's keyword arguments; its defaults are 1.0, 200.0, 400, 6371.0)
+ *   scalars_out [n_rays x 5]: group_path_km, group_delay_sec, x_midpoint, z_midpoint, ground_range_km
+ *   (the reference's x_apex_km / z_apex_km repeat the midpoint, library.py:1267-1268); NaN when there is no ray
+ *   x_out, z_out [n_rays x path_stride] (both or neither; path_stride >= 2 (n_alt + 1) + 1): the ray path,
+ *   NaN-padded; n_path_out [n_rays] (may be NULL): points on the path, 0 = no ray.
+ */
+int prhf_snell_f64(prhf_ctx* ctx, const double* f0_hz, const double* elevation_deg, int64_t n_rays,
+                   const double* alt_km, const double* ne, const double* babs, const double* bpsi, int n_alt, int mode,
+                   int geometry, unsigned flags, double dz_target_km, double apex_boost, int max_substeps, double r_e_km,
+                   double* scalars_out, double* x_out, double* z_out, int path_stride, int* n_path_out,
+                   void* cuda_stream);
+
+/*
  * Residual of the inversion objective on DEVICE buffers (replaces the arithmetic tail of residual_VH,
  * library.py:660-668, for a batch of candidate profiles): NaN model heights are replaced by
  * max(nanmean|vh_model[p,:]|, 100) (library.py:664-665), residual = vh_obs - vh_model (library.py:668).

@@ -32,3 +32,9 @@ from pyrayhf_b200.stages import (  # noqa: E402,F401
     regrid_to_nonuniform_grid,
     find_vh,
 )
+from pyrayhf_b200 import snell  # noqa: E402,F401
+from pyrayhf_b200.snell import (  # noqa: E402,F401
+    trace_ray_cartesian_snells,
+    trace_ray_spherical_snells,
+    trace_rays_snells_batched,
+)

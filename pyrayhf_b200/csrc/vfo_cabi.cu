@@ -847,6 +847,47 @@ int prhf_synth_profiles_f64(prhf_ctx* ctx, const double* params, int64_t n_profi
   return PRHF_OK;
 }
 
+int prhf_snell_f64(prhf_ctx* ctx, const double* f0_hz, const double* elevation_deg, int64_t n_rays,
+                   const double* alt_km, const double* ne, const double* babs, const double* bpsi, int n_alt, int mode,
+                   int geometry, unsigned flags, double dz_target_km, double apex_boost, int max_substeps, double r_e_km,
+                   double* scalars_out, double* x_out, double* z_out, int path_stride, int* n_path_out,
+                   void* cuda_stream) {
+  if (!ctx || n_rays < 0 || n_alt < 1) return PRHF_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return PRHF_ERR_BAD_MODE;
+  if (geometry != 0 && geometry != 1) return PRHF_ERR_INVALID_ARG;
+  if (n_rays == 0) return PRHF_OK;
+  if (!f0_hz || !elevation_deg || !alt_km || !ne || !babs || !bpsi || !scalars_out) return PRHF_ERR_INVALID_ARG;
+  if ((x_out == nullptr) != (z_out == nullptr)) return PRHF_ERR_INVALID_ARG;
+  if (x_out && path_stride < 2 * (n_alt + 1) + 1) return PRHF_ERR_INVALID_ARG;
+  if (geometry == 1 && (!(dz_target_km > 0.0) || max_substeps < 1)) return PRHF_ERR_INVALID_ARG;
+  if (prhf::snell_smem_bytes(n_alt) > (size_t)ctx->max_smem_optin) return PRHF_ERR_NALT_TOO_LARGE;
+  DeviceGuard g(ctx->device);
+  prhf::SnellParams P;
+  P.f0_hz = f0_hz;
+  P.elev_deg = elevation_deg;
+  P.n_rays = n_rays;
+  P.alt = alt_km;
+  P.ne = ne;
+  P.babs = babs;
+  P.bpsi = bpsi;
+  P.n_alt = n_alt;
+  P.mode = mode;
+  P.spherical = geometry;
+  P.literal = (flags & PRHF_FLAG_LITERAL) ? 1 : 0;
+  P.dz_target = dz_target_km;
+  P.apex_boost = apex_boost;
+  P.max_substeps = max_substeps;
+  P.r_e = r_e_km;
+  P.scalars = scalars_out;
+  P.x_out = x_out;
+  P.z_out = z_out;
+  P.path_stride = path_stride;
+  P.n_path = n_path_out;
+  PRHF_CUDA(ctx, prhf::launch_snell(P, ctx->max_smem_optin, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
 int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_obs, int64_t n_profiles, int n_freq,
                       double* residual_out, double* chi2_out, void* cuda_stream) {
   if (!ctx || n_profiles < 0 || n_freq < 0) return PRHF_ERR_INVALID_ARG;

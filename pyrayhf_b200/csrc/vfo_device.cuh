@@ -220,4 +220,35 @@ __device__ __forceinline__ void rotate_sincos_small(double sk, double ck, double
 }
 constexpr double kSmallRotateStep = 4e-4;
 
+// ---- numpy arr_interp for one query against the staged altitude axis (left = fp[0], right = fp[n-1]) ----
+// Returns the bracket: -2 NaN query, -1 below the axis, n above it, else the last j with xp[j] <= x.
+__device__ __forceinline__ int np_bracket(double x, const double* __restrict__ xp, int n) {
+  if (x != x) return -2;
+  if (x < xp[0]) return -1;
+  if (x > xp[n - 1]) return n;
+  int lo = 0, hi = n - 1;                                   // xp[lo] <= x <= xp[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xp[mid] <= x) lo = mid; else hi = mid;
+  }
+  return (xp[hi] <= x) ? hi : lo;
+}
+__device__ __forceinline__ double np_interp_at(double x, int j, const double* __restrict__ xp,
+                                               const double* __restrict__ fp, int n) {
+  if (n == 1) return fp[0];                                 // numpy's single-node branch has no NaN test
+  if (j == -2) return x;
+  if (j == -1) return fp[0];
+  if (j >= n - 1) return fp[n - 1];
+  const double x0 = xp[j], f0 = fp[j];
+  if (x0 == x) return f0;
+  const double x1 = xp[j + 1], f1 = fp[j + 1];
+  const double slope = __ddiv_rn(__dsub_rn(f1, f0), __dsub_rn(x1, x0));
+  double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, x0)), f0);
+  if (r != r) {                                             // numpy's NaN rescue
+    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, x1)), f1);
+    if (r != r && f0 == f1) r = f0;
+  }
+  return r;
+}
+
 }  // namespace prhf

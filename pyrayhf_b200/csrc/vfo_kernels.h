@@ -126,6 +126,25 @@ cudaError_t launch_regrid_write(const RegridParams& p, int n_alt, cudaStream_t s
 cudaError_t launch_find_vh(const double* X, const double* Y, const double* psi, const double* dh, int64_t n_rows,
                            int64_t n_cols, double alt_min, int mode, bool literal, unsigned long long* scratch_word,
                            double* vh, cudaStream_t stream);
+// stratified Snell's-law tracers (vfo_snell.cu)
+struct SnellParams {
+  const double* f0_hz;     // [n_rays]
+  const double* elev_deg;  // [n_rays]
+  int64_t n_rays;
+  const double *alt, *ne, *babs, *bpsi;   // one profile, [n_alt]
+  int n_alt;
+  int mode, spherical, literal;
+  double dz_target, apex_boost;
+  int max_substeps;
+  double r_e;
+  double* scalars;         // [n_rays x 5]: group path km, group delay s, x midpoint, z midpoint, ground range km
+  double* x_out;           // optional [n_rays x path_stride] (NaN-padded), with z_out
+  double* z_out;
+  int path_stride;
+  int* n_path;             // optional [n_rays]: points on the path, 0 = no ray (every output NaN)
+};
+size_t snell_smem_bytes(int n_alt);
+cudaError_t launch_snell(const SnellParams& p, int max_smem_optin, cudaStream_t stream);
 cudaError_t launch_synth_profiles(const double* params, int64_t n_profiles, const double* alt, int n_alt, double* den,
                                   double* bmag, double* bpsi, cudaStream_t stream);
 cudaError_t launch_dfma_probe(double* out, int blocks, int iters, cudaStream_t stream);
