@@ -158,6 +158,80 @@ def measured_peaks():
         return {}
 
 
+def next_rows_section(torch, dev, stream, ctx, freq, den, bmag, bpsi, alt, with_cpu):
+    """Throughput of the operators beside the headline path: the standalone regrid stage
+    (HBM-bound), the batched Snell's-law tracers and the inversion residual.  Device-resident inputs, CUDA events
+    on the launching stream, L2 flushed by the caller's buffer between repetitions is not needed here: every
+    repetition streams more than L2 (regrid) or is compute-bound (tracers)."""
+    import ctypes
+    vp = ctypes.c_void_p
+    L = ctx.lib
+    sp = vp(stream.cuda_stream)
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)   # noqa: E731
+    out = {}
+    # ---- regrid_to_nonuniform_grid: five [F x N] arrays written ----
+    n_freq, n_pts = freq.size, N_POINTS
+    tf, td, tb, tp, ta = t(freq * 1e6), t(den), t(bmag), t(bpsi), t(alt)
+    hc = torch.empty(n_freq, dtype=torch.float64, device=dev)
+    big = [torch.empty((n_freq, n_pts), dtype=torch.float64, device=dev) for _ in range(5)]
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ctx.check(L.prhf_regrid_f64(ctx.handle, vp(tf.data_ptr()), n_freq, vp(td.data_ptr()),
+                                                   vp(tb.data_ptr()), vp(tp.data_ptr()), vp(ta.data_ptr()), alt.size, 1,
+                                                   n_pts, vp(hc.data_ptr()), *[vp(b.data_ptr()) for b in big],
+                                                   vp(st.data_ptr()), sp)))
+    hbm_peak = measured_peaks().get("hbm_gbs", 6544.7)
+    gbs = 5 * n_freq * n_pts * 8 / (ms * 1e-3) / 1e9
+    out["regrid_stage"] = {"workload": "regrid_to_nonuniform_grid, %d freqs x %d points, 5 arrays written" % (n_freq, n_pts),
+                           "ms": ms, "write_GBps": gbs, "frac_of_measured_hbm": gbs / hbm_peak,
+                           "note": "row-setup kernel + write kernel; bound = HBM writes (MEASURED_PEAKS.json hbm_gbs)"}
+    # ---- Snell tracers: 174 frequencies x 64 elevations over the same profile ----
+    elev = np.linspace(5.0, 88.0, 64)
+    f_r = np.repeat(freq * 1e6, elev.size)
+    e_r = np.tile(elev, freq.size)
+    t_f, t_e = t(f_r), t(e_r)
+    scal = torch.empty((f_r.size, 5), dtype=torch.float64, device=dev)
+    npth = torch.zeros(f_r.size, dtype=torch.int32, device=dev)
+    for geo, name in ((0, "cartesian"), (1, "spherical")):
+        ms = timed(lambda: ctx.check(L.prhf_snell_f64(ctx.handle, vp(t_f.data_ptr()), vp(t_e.data_ptr()), f_r.size,
+                                                      vp(ta.data_ptr()), vp(td.data_ptr()), vp(tb.data_ptr()),
+                                                      vp(tp.data_ptr()), alt.size, 1, geo, 0, 1.0, 200.0, 400, 6371.0,
+                                                      vp(scal.data_ptr()), None, None, 0, vp(npth.data_ptr()), sp)))
+        entry = {"rays": int(f_r.size), "rays_with_a_path": int((npth > 0).sum().item()), "ms": ms,
+                 "rays_per_s": f_r.size / (ms * 1e-3)}
+        if with_cpu:
+            from oracle import snell_oracle
+            idx = np.linspace(0, f_r.size - 1, 12).astype(int)
+            t0 = time.perf_counter()
+            for i in idx:
+                snell_oracle.trace(f_r[i], e_r[i], alt, den, bmag, bpsi, 'X', name)
+            cpu = (time.perf_counter() - t0) / idx.size
+            entry["cpu_port_rays_per_s_1_core"] = 1.0 / cpu
+        out["snell_" + name] = entry
+    # ---- inversion residual: chi2 of 4096 candidate curves ----
+    vm = torch.rand((4096, n_freq), dtype=torch.float64, device=dev) * 300 + 100
+    vo = torch.rand(n_freq, dtype=torch.float64, device=dev) * 300 + 100
+    chi = torch.empty(4096, dtype=torch.float64, device=dev)
+    ms = timed(lambda: ctx.check(L.prhf_residual_f64(ctx.handle, vp(vm.data_ptr()), vp(vo.data_ptr()), 4096, n_freq,
+                                                     None, vp(chi.data_ptr()), sp)))
+    out["residual_chi2"] = {"candidates": 4096, "ms": ms, "read_GBps": 4096 * n_freq * 8 / (ms * 1e-3) / 1e9}
+    return out
+
+
 def run_b200_arm(args):
     import ctypes
     import torch
@@ -344,6 +418,10 @@ def run_b200_arm(args):
         if batched:
             batched["tile_kernel_frac_of_fp64_peak"] = batched["tile_kernel_tflops"] / peak_tf
             line["batched"] = batched
+        if world == 1 and not args.no_batched:
+            warnings.simplefilter("ignore")
+            line["next_rows"] = next_rows_section(torch, dev, stream, ctx, freq, den, bmag, bpsi, alt,
+                                                  with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             warnings.simplefilter("ignore")
             cb = cpu_numpy_port(steps=2, warmup=0, budget_s=30.0)
