@@ -53,13 +53,13 @@ __device__ __forceinline__ int trace_smid() {
 
 // ------------------------------------------------------------------------------------------
 // stretched-grid multiplier table (lib:314-320): m_i = 1 - (exp(10 (1-u_i)) - 1)/(exp(10) - 1)
-// The table has kMultPad extra entries (value 1) so that the main loop can read m[i+1], m[i+2]
-// unconditionally.
+// The table has kMultPad extra entries (copies of the last entry) so that the main loop can read m[i+1],
+// m[i+2] unconditionally and the row's last point gets the in-loop weight h(pad) - h(last) = 0.
 // ------------------------------------------------------------------------------------------
 __global__ void grid_multiplier_kernel(int n, int n_padded, double step, double* __restrict__ m) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded) return;
-  if (i >= n) { m[i] = 1.0; return; }
+  if (i >= n) { m[i] = (n > 1) ? 1.0 : 0.0; return; }    // copies of the last entry m[n-1]
   double u = __dmul_rn((double)i, step);        // np.linspace: arange(n) * step ...
   if (i == n - 1 && n > 1) u = 1.0;             // ... with the endpoint forced
   const double fl = __dsub_rn(1.0, u);
@@ -401,7 +401,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     // finite <=> (x - x) == 0
     if (!(((d - d) + (b - b)) + ((ps - ps) + (a - a)) == 0.0)) chk |= 2;
     bmax = fmax(bmax, fabs(b));
-    if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 0.25 * mean_step)) chk |= 4;
+    if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 2e-15 * fmax(fabs(a), mean_step))) chk |= 4;   // ~8 ulp
     if (!(a > 0.0)) chk |= 2;                           // the fast paths compare altitudes as integers
     if (k + 1 < nt) {
       if (!(__dsub_rn(s_alt[k + 1], a) > 0.0)) chk |= 2;
@@ -901,16 +901,14 @@ __device__ __forceinline__ double fast_point(double h, int j, const Node* nodes,
   return ah_hot<MODE>(X, (Y * sn) * 0.70710678118654752, Y * cs, mu_out);
 }
 
-// Branch-free bracket for altitude grids K1 flagged uniform (every level within a quarter step of
-// alt0 + k * mean step): floor((h - alt0) / step) is the bracket or one off, two integer compares decide.
-__device__ __forceinline__ int bracket_uniform(double h, const Node* nodes, int jlo, int jhi, int guess) {
-  const int j = min(max(guess, jlo), jhi - 1);                        // jhi > jlo on this path
-  const long long hb = __double_as_longlong(h);
-  const long long* alt = reinterpret_cast<const long long*>(&nodes[0].alt) + (ptrdiff_t)(j - jlo) * 8;
-  const int down = (hb < alt[0]) ? 1 : 0;
-  const int up = (hb >= alt[8]) ? 1 : 0;
-  return max(j + up - down, jlo);
-}
+// Bracket for altitude grids K1 flagged uniform (every level within ~8 ulp of alt0 + k * mean step, e.g. any
+// np.arange / np.linspace grid): floor((h - alt0) / step), clamped to the staged window, with NO verification
+// against the node altitudes.  The guess can only be off by one when h lies within ~1e-12 km of a level; the
+// piecewise-linear interpolants are continuous there, so evaluating the neighbouring segment changes X, Y by
+// |h - level| * |slope difference| < 1e-13 relative -- four orders below the parity tolerance -- while the
+// verification cost 10 of the loop's 187 instructions per point pair.  Grids that are merely close to uniform
+// take find_bracket_pos (guess, verify, binary search).
+__device__ __forceinline__ int bracket_uniform(int jlo, int jhi, int guess) { return min(max(guess, jlo), jhi); }
 
 template <int MODE, int PATH, bool UNIFORM, bool ROWSCALE>
 __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
@@ -918,19 +916,37 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
   double acc0 = 0.0, acc1 = 0.0;
   const double2* m2 = reinterpret_cast<const double2*>(m);
   const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
+  // The tile kernels (long segments) read the multiplier table one iteration ahead, so that the L2 / L1 latency of
+  // the load overlaps the ~95 FP64 instructions of the current pair of points (+3.9 % on batches, measured:
+  // profiles/sweep_mpref_r01.log).  The row-per-warp kernel (<= 4096 points per row, 2-3 iterations per thread)
+  // loses from the extra prologue load and keeps the plain form.
+  constexpr bool kAhead = !ROWSCALE;
+  double2 mm_next = make_double2(1.0, 1.0);
+  double mn_next = 1.0;
+  if (kAhead) {
+    const int ip = i0 + 2 * rc.lane0;
+    if (ip < i1) { mm_next = __ldg(m2 + (ip >> 1)); mn_next = __ldg(m + ip + 2); }
+  }
   for (int i = i0 + 2 * rc.lane0; i < i1; i += 2 * rc.group) {
-    const double2 mm = __ldg(m2 + (i >> 1));                         // i0 is even, the table is padded
-    const double mn = __ldg(m + i + 2);
+    double2 mm;
+    double mn;
+    if (kAhead) {
+      mm = mm_next;
+      mn = mn_next;
+      const int in = i + 2 * rc.group;
+      if (in < i1) { mm_next = __ldg(m2 + (in >> 1)); mn_next = __ldg(m + in + 2); }
+    } else {
+      mm = __ldg(m2 + (i >> 1));                                     // i0 is even, the table is padded
+      mn = __ldg(m + i + 2);
+    }
     const double h0 = fma(mm.x, rc.span, rc.alt0);                   // lib:413
     const double h1 = fma(mm.y, rc.span, rc.alt0);
     const double h2 = fma(mn, rc.span, rc.alt0);
-    double dh0 = h1 - h0, dh1 = h2 - h1;                             // lib:415
-    if (i == n_points - 1) dh0 = kBackoff;                           // lib:416
-    if (i + 1 == n_points - 1) dh1 = kBackoff;
+    const double dh0 = h1 - h0, dh1 = h2 - h1;                       // lib:415; 0 for the row's last point (padded table)
     int j0, j1;
     if (UNIFORM) {
-      j0 = bracket_uniform(h0, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
-      j1 = bracket_uniform(h1, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.y * c1));
+      j0 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
+      j1 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.y * c1));
     } else {
       j0 = find_bracket_pos(h0, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
       j1 = find_bracket_pos(h1, nodes, rc.jlo, rc.jhi, j0);
@@ -940,6 +956,18 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
     const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1);
     acc0 = fma(keep_term(mu0, p0) ? p0 : 0.0, dh0, acc0);            // nansum (lib:288)
     acc1 = fma((keep_term(mu1, p1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
+  }
+  // lib:416: the row's last grid point weighs 1e-6.  The table is padded with copies of its last entry, so that
+  // point entered the loop with weight 0; its owner adds the term here instead of two selects per iteration.
+  const int il = n_points - 1, ip = il & ~1;
+  if (ip >= i0 && ip < i1 && ((ip - i0) >> 1) % rc.group == rc.lane0) {
+    const double ml = __ldg(m + il);
+    const double hl = fma(ml, rc.span, rc.alt0);
+    const int g = __double2int_rd(ml * c1);
+    const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, g) : find_bracket_pos(hl, nodes, rc.jlo, rc.jhi, g);
+    double mul;
+    const double pl = fast_point<MODE, PATH, ROWSCALE>(hl, jl, nodes, rc, &mul);
+    acc0 = fma(keep_term(mul, pl) ? pl : 0.0, kBackoff, acc0);
   }
   return acc0 + acc1;
 }
