@@ -93,6 +93,16 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
   return fma(y, e * fma(e, 0.375, 0.5), y);            // y (1 + e/2 + 3 e^2 / 8)
 }
 
+// ---- per-row scale factors of the screen and the fast paths: X = den * kx, Y = b * ky ----
+// (never used where the reference's rounding order matters: those places call x_literal / y_literal.)
+// Reciprocals through rcp_fast instead of IEEE division: a division is ~400 cycles of pure latency and the row
+// prologue used to have six of them back to back on its critical path.  Relative error <= 5e-16.
+__device__ __forceinline__ void row_scales(double f_hz, double* kx, double* ky) {
+  const double af = fabs(f_hz);
+  *kx = (kCp * kCp) * rcp_fast(af * af);
+  *ky = copysign(kGp * rcp_fast(af), f_hz);
+}
+
 // ---- restructured Appleton-Hartree: same formulas as lib:209-254, algebraically rearranged ----
 //   a = YT^2/2, w = YL^2 Xm1, alpha = a^2 + w Xm1, beta = sqrt(alpha), P = a + beta
 //   X-mode:  D = Xm1 - P                      (no cancellation: D -> Y(1-Y) at reflection)

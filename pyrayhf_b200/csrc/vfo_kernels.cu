@@ -42,6 +42,10 @@ __device__ __forceinline__ int trace_smid() {
   asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
   return s;
 }
+#define PRHF_TRACE_X(slot)                                                                                   \
+  do {                                                                                                     \
+    if (p.trace_k1 && threadIdx.x == 0) p.trace_k1[16384 + (size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
 #define PRHF_TRACE_K1(slot)                                                                      \
   do {                                                                                           \
     if (p.trace_k1 && threadIdx.x == 0) p.trace_k1[(size_t)blockIdx.x * 8 + (slot)] = clock64(); \
@@ -49,6 +53,7 @@ __device__ __forceinline__ int trace_smid() {
 #else
 #define PRHF_TRACE_MARK(slot) do { } while (0)
 #define PRHF_TRACE_K1(slot) do { } while (0)
+#define PRHF_TRACE_X(slot) do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -365,17 +370,37 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   double best_v = -CUDART_INF;
   int best_i = 0x7fffffff;
   double amin = CUDART_INF;
-  for (int k = tid; k < A; k += kThreads) {
-    const double d = g_den[k];
-    const double a = g_alt[k];
-    const double b = g_b[k];
-    const double ps = g_psi[k];
-    s_den[k] = d;
-    s_alt[k] = a;
-    s_b[k] = b;
-    s_psi[k] = ps;
-    if (arg_precedes(d, k, best_v, best_i)) { best_v = d; best_i = k; }
-    amin = fmin(amin, a);
+  {
+    // the first kPre levels of every thread are loaded into registers before anything consumes them: with a
+    // plain loop the argmax test made every trip wait for its own DRAM round trip (3 in a row for 620 levels)
+    constexpr int kPre = 3;
+    double d[kPre], a[kPre], b[kPre], ps[kPre];
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int k = tid + u * kThreads;
+      if (k < A) { d[u] = g_den[k]; a[u] = g_alt[k]; b[u] = g_b[k]; ps[u] = g_psi[k]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int k = tid + u * kThreads;
+      if (k < A) {
+        s_den[k] = d[u];
+        s_alt[k] = a[u];
+        s_b[k] = b[u];
+        s_psi[k] = ps[u];
+        if (arg_precedes(d[u], k, best_v, best_i)) { best_v = d[u]; best_i = k; }
+        amin = fmin(amin, a[u]);
+      }
+    }
+    for (int k = tid + kPre * kThreads; k < A; k += kThreads) {
+      const double dk = g_den[k], ak = g_alt[k], bk = g_b[k], pk = g_psi[k];
+      s_den[k] = dk;
+      s_alt[k] = ak;
+      s_b[k] = bk;
+      s_psi[k] = pk;
+      if (arg_precedes(dk, k, best_v, best_i)) { best_v = dk; best_i = k; }
+      amin = fmin(amin, ak);
+    }
   }
   PRHF_TRACE_K1(1);
   __shared__ long long s_key[kThreads / 32];
@@ -391,7 +416,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   int chk = 0;                                          // bit 0 negative density, 1 general path, 2 non-uniform grid
   double bmax = 0.0, step_max = 0.0;
   const double alt0 = s_alt[0];
-  const double mean_step = (nt > 1) ? (s_alt[nt - 1] - alt0) / (double)(nt - 1) : 1.0;
+  const double mean_step = (nt > 1) ? (s_alt[nt - 1] - alt0) * rcp_fast((double)(nt - 1)) : 1.0;
   for (int k = tid; k < nt; k += kThreads) {
     const double d = s_den[k];
     const double b = s_b[k];
@@ -410,8 +435,10 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       step_max = fmax(step_max, step);
     }
   }
+  PRHF_TRACE_X(0);
   __syncthreads();                                      // s_key/s_ri/s_ra are free again
   const ProfileReduce2 r2 = block_max2_or(bmax, step_max, chk, s_ra, s_rb, s_ri);
+  PRHF_TRACE_X(1);
   bmax = r2.bmax;
   step_max = r2.step_max;
   const bool any_neg = (r2.flags & 1) != 0;
@@ -440,7 +467,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
                 (step_max == 0.0 ? kFlagPsiConst : 0) | (step_max <= kSmallRotateStep ? kFlagPsiSmall : 0) |
                 (any_nonuniform ? 0 : kFlagUniformAlt);
     rec.alt_min = alt_min;
-    rec.inv_dalt = (nt > 1) ? (double)(nt - 1) / (s_alt[nt - 1] - alt0) : 0.0;
+    rec.inv_dalt = (nt > 1) ? (double)(nt - 1) * rcp_fast(s_alt[nt - 1] - alt0) : 0.0;
     rec.alt0 = alt0;
     sincos(s_psi[0] * kDeg2Rad, &rec.sn0, &rec.cs0);
     rec.pad[0] = rec.pad[1] = 0.0;
@@ -470,8 +497,9 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       return;
     }
     const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], p.freq_scale);   // lib:491
-    const double kx = (kCp * kCp) / __dmul_rn(f_hz, f_hz);
-    const double ky = (mode == 1) ? kGp / f_hz : 0.0;
+    double kx, ky;
+    row_scales(f_hz, &kx, &ky);
+    if (mode != 1) ky = 0.0;
     bool slow = any_general || !(isfinite(kx) && isfinite(ky) && kx > 0.0);
     int jstar = 0x7fffffff;
     bool any_eq1 = false, has_nan = false;
@@ -566,8 +594,9 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   if (p.k1_solo) {
     if (tid == 0) s_solo_quick = 0;
     const double f_hz0 = __dmul_rn(p.freq[prof * p.freq_stride + g], p.freq_scale);
-    const double kx0 = (kCp * kCp) / __dmul_rn(f_hz0, f_hz0);
-    const double ky0 = (mode == 1) ? kGp / f_hz0 : 0.0;
+    double kx0, ky0;
+    row_scales(f_hz0, &kx0, &ky0);
+    if (mode != 1) ky0 = 0.0;
     const bool screen0 = status == 0 && !any_general && isfinite(kx0) && isfinite(ky0) && kx0 > 0.0;
     if (screen0) {                                        // block-uniform
       int my_cand = 0x7fffffff;
@@ -575,6 +604,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
         const double xk = s_den[k] * kx0, yk = s_b[k] * ky0;
         if (my_cand == 0x7fffffff && xk + yk >= 1.0 - kScreenTol * (fabs(xk) + fabs(yk))) my_cand = k;
       }
+      PRHF_TRACE_X(3);
       my_cand = warp_min_i(my_cand);
       __syncthreads();
       if (lane == 0) s_ri[wid] = my_cand;
@@ -582,6 +612,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       int cand = s_ri[0];
 #pragma unroll
       for (int k = 1; k < kThreads / 32; ++k) cand = min(cand, s_ri[k]);
+      PRHF_TRACE_X(4);
       if (cand == 0x7fffffff) {
         if (tid == 0) { s_solo_cand = cand; s_solo_quick = 1; }   // no level can reach 1: no reflection
       } else {
@@ -598,6 +629,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
           const double xk = s_den[k] * kx0, yk = s_b[k] * ky0;
           deep = fmax(deep, xk + yk + kScreenTol * (fabs(xk) + fabs(yk)));
         }
+        PRHF_TRACE_X(5);
         double below = (kw >= 0 && kw < cand) ? v : -CUDART_INF;
         below = warp_max(below);
         deep = warp_max(deep);
@@ -616,6 +648,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       }
     }
     __syncthreads();
+    PRHF_TRACE_X(6);
   }
 
   // ---- one warp per sounding frequency, p.rows_per_warp frequencies per warp ----
@@ -642,8 +675,9 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     // a_k = den_k * (cp^2/f^2) + b_k * (g_p/f), whose distance from the literal value is bounded by
     // 13 ulp * (|X_k| + |Y_k|); only nodes whose screen value is within kScreenTol of a decision are
     // evaluated literally, so every decision and every value that enters h_c is the literal one.
-    const double kx = (kCp * kCp) / __dmul_rn(f_hz, f_hz);
-    const double ky = (mode == 1) ? kGp / f_hz : 0.0;
+    double kx, ky;
+    row_scales(f_hz, &kx, &ky);
+    if (mode != 1) ky = 0.0;
     const bool screen = !any_general && isfinite(kx) && isfinite(ky) && kx > 0.0;
     int jstar = 0x7fffffff;
     bool any_eq1 = false, has_nan = false;
@@ -1134,9 +1168,10 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   rc.span = span;
   rc.inv_dalt = rec.inv_dalt;
   rc.nt = nt;
-  const double kx = (kCp * kCp) / (rc.f_hz * rc.f_hz);    // fast paths: X = den * kx, Y = b * ky
-  const double ky = kGp / rc.f_hz;
+  double kx, ky;                                          // fast paths: X = den * kx, Y = b * ky
+  row_scales(rc.f_hz, &kx, &ky);
   const bool const_mup = !(span > 0.0) || nt == 1;         // h_c <= alt0: every point clamps to level 0
+  PRHF_TRACE_X(10);
 
   // ---- node window of this tile: brackets of its first and last grid point ----
   if (const_mup) {
@@ -1315,8 +1350,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
     rc.span = span;
     rc.inv_dalt = rec.inv_dalt;
     rc.nt = nt;
-    rc.kx = (kCp * kCp) / (rc.f_hz * rc.f_hz);
-    rc.ky = kGp / rc.f_hz;
+    row_scales(rc.f_hz, &rc.kx, &rc.ky);
     rc.lane0 = lane;
     rc.group = 32;
     const bool const_mup = !(span > 0.0) || nt == 1;       // h_c <= alt0: every point clamps to level 0
@@ -1344,6 +1378,25 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_solo_kernel(
   __shared__ double s_span;
   const int64_t tile = blockIdx.x;
   const int64_t lrow = tile / p.n_seg;
+  {
+    // Everything this CTA will read later from cold memory is requested now, so that the DRAM round trips overlap
+    // the profile staging instead of following it one by one: the row's frequency, the ends of the tile's
+    // multiplier segment (window computation) and the segment itself (first touch in the grid loop).
+    const int seg = (int)(tile % p.n_seg);
+    const int i0 = seg * p.seg_len, i1 = min(p.n_points, i0 + p.seg_len);
+    const int64_t prof = p.profile_offset + lrow / p.n_freq;
+    if (threadIdx.x == 0) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.freq + prof * p.freq_stride + lrow % p.n_freq));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mult + i0));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mult + max(i1 - 1, i0)));
+    }
+    // the rows of a profile share the segment: each CTA requests only its own slice of the lines, so the segment
+    // is pulled into L2 once instead of once per row
+    const char* mseg = reinterpret_cast<const char*>(p.mult + i0);
+    const int n_lines = (int)(((size_t)(i1 - i0 + kMultPad) * sizeof(double) + 127) / 128);
+    const int line = (int)(lrow % p.n_freq) + (int)threadIdx.x * p.n_freq;
+    if (line < n_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(mseg + (size_t)line * 128));
+  }
   if (threadIdx.x == 0) s_span = CUDART_NAN;
   rows_body(p, MODE, lrow, reinterpret_cast<double*>(smem_raw), sc, &s_rec, &s_span);   // syncs internally
   __syncthreads();

@@ -37,6 +37,9 @@ def main():
     out = np.zeros((n_tiles + 4096, 8), dtype=np.int64)
     L.prhf_debug_trace_read(ctx.handle, n_tiles, vp(out.ctypes.data))
     k1 = out[n_tiles:]
+    extra = k1.reshape(-1)[16384:16384 + 16 * 1024].reshape(-1, 16)
+    k1 = k1[:1024]
+    extra = extra[:len(k1)][k1[:, 0] != 0]
     k1 = k1[k1[:, 0] != 0]
     out = out[:n_tiles]
     print('K1 CTAs', len(k1))
@@ -46,6 +49,19 @@ def main():
         d = k1[:, b] - k1[:, a]
         print('  K1 %-12s cycles: median %6.0f max %6.0f' % (nm, np.median(d), d.max()))
     print('  K1 CTA total median %d max %d' % (np.median(k1[:, 4] - k1[:, 0]), (k1[:, 4] - k1[:, 0]).max()))
+    def seg(name, a, b):
+        ok = (a != 0) & (b != 0)
+        if ok.any():
+            print('    %-34s median %6.0f  (n=%d)' % (name, np.median((b - a)[ok]), ok.sum()))
+    seg('argmax end -> checks loop end', k1[:, 2], extra[:, 0])
+    seg('checks reduction', extra[:, 0], extra[:, 1])
+    seg('record + sync', extra[:, 1], k1[:, 3])
+    seg('solo: kx/ky + screen loop', k1[:, 3], extra[:, 3])
+    seg('solo: first reduction', extra[:, 3], extra[:, 4])
+    seg('solo: literal eval + deep loop', extra[:, 4], extra[:, 5])
+    seg('solo: second reduction', extra[:, 5], extra[:, 6])
+    seg('solo: h_c + stores', extra[:, 6], k1[:, 4])
+    seg('tile: K1 end -> row constants', k1[:, 4], extra[:, 10])
     used = out[:, 1] != 0
     tr = out[used]
     live = tr[:, 7] != 0
