@@ -633,6 +633,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
         double below = (kw >= 0 && kw < cand) ? v : -CUDART_INF;
         below = warp_max(below);
         deep = warp_max(deep);
+        PRHF_TRACE_X(9);
         __syncthreads();
         if (lane == 0) { s_ra[wid] = below; s_rb[wid] = deep; }
         if (kw == cand) s_solo_vc = v;
@@ -682,6 +683,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     int jstar = 0x7fffffff;
     bool any_eq1 = false, has_nan = false;
     double v_jstar = 0.0, M = -CUDART_INF;
+    PRHF_TRACE_X(7);
     if (p.k1_solo && s_solo_quick) {
       jstar = s_solo_cand;
       v_jstar = s_solo_vc;
@@ -720,6 +722,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
         hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
       }
     }
+    PRHF_TRACE_X(8);
     if (lane == 0) {
       const double hc = __dsub_rn(hcrit, kBackoff);         // lib:407
       const double span = __dsub_rn(hc, s_alt[0]);          // lib:413 (h_c - aalt[0])
@@ -1392,6 +1395,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_solo_kernel(
     }
     // the rows of a profile share the segment: each CTA requests only its own slice of the lines, so the segment
     // is pulled into L2 once instead of once per row
+    // ... and the second line of the kernel parameters (cold constant bank), whose first reader would otherwise be
+    // the row scan
+    asm volatile("" ::"d"(p.freq_scale), "l"(p.row_span), "l"(p.partial));
     const char* mseg = reinterpret_cast<const char*>(p.mult + i0);
     const int n_lines = (int)(((size_t)(i1 - i0 + kMultPad) * sizeof(double) + 127) / 128);
     const int line = (int)(lrow % p.n_freq) + (int)threadIdx.x * p.n_freq;

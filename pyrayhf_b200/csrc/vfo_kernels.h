@@ -83,13 +83,16 @@ struct VfoParams {
   int max_seg;             // stride of `partial` per row; planner's upper bound on n_seg
   int slots;               // resident tile-kernel CTAs on the device
   int n_sm, ctas_per_sm;   // its factors
-  int n_cand;              // planner candidates: (segments per row, grid points per segment)
-  int cand_seg[kMaxPlanCand];
-  int cand_len[kMaxPlanCand];
   long long* trace_k1;     // developer phase trace of K1 [ctas x 8] (PRHF_TRACE builds), else null
   double freq_scale;       // row setup: f_hz = freq * freq_scale (1e6 for MHz input, lib:491; 1 for the Hz input of
                            // the standalone regrid stage).  The tile kernels always assume MHz.
   double* row_hc;          // optional [rows_in_launch]: reflection height h_c (lib:407), NaN on rows without one
+  // Kernel parameters sit in a constant bank that is cold at every launch; each 128-byte line of this struct costs
+  // its first reader a miss.  Everything the single-profile path touches stays above this comment (two lines);
+  // the planner's candidate tables (256 bytes, planned mode only) come last.
+  int n_cand;              // planner candidates: (segments per row, grid points per segment)
+  int cand_seg[kMaxPlanCand];
+  int cand_len[kMaxPlanCand];
 };
 
 size_t vfo_smem_bytes(int n_alt);

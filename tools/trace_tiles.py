@@ -59,8 +59,11 @@ def main():
     seg('solo: kx/ky + screen loop', k1[:, 3], extra[:, 3])
     seg('solo: first reduction', extra[:, 3], extra[:, 4])
     seg('solo: literal eval + deep loop', extra[:, 4], extra[:, 5])
-    seg('solo: second reduction', extra[:, 5], extra[:, 6])
-    seg('solo: h_c + stores', extra[:, 6], k1[:, 4])
+    seg('solo: second reduction shuffles', extra[:, 5], extra[:, 9])
+    seg('solo: second reduction barrier+', extra[:, 9], extra[:, 6])
+    seg('solo: -> row scales (warp loop)', extra[:, 6], extra[:, 7])
+    seg('solo: -> h_c', extra[:, 7], extra[:, 8])
+    seg('solo: stores', extra[:, 8], k1[:, 4])
     seg('tile: K1 end -> row constants', k1[:, 4], extra[:, 10])
     used = out[:, 1] != 0
     tr = out[used]
