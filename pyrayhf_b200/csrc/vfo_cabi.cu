@@ -215,10 +215,12 @@ struct CallMode {
 };
 CallMode call_mode(const prhf_ctx* ctx, int64_t rows_total, int n_points, int n_alt) {
   CallMode m;
-  m.ctas_per_sm = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm);
-  m.slots = ctx->sm_count * m.ctas_per_sm;
   const bool small = use_planned_mode(ctx, rows_total, n_points);
-  m.solo = ctx->use_solo && small && rows_total * 2 <= m.slots;
+  // the single-launch kernel keeps fewer CTAs resident (it carries the row setup): decide with its own slot count
+  const int solo_ctas = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm, true);
+  m.solo = ctx->use_solo && small && rows_total * 2 <= (int64_t)ctx->sm_count * solo_ctas;
+  m.ctas_per_sm = m.solo ? solo_ctas : prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm, false);
+  m.slots = ctx->sm_count * m.ctas_per_sm;
   m.planned = small && !m.solo;
   return m;
 }

@@ -1374,7 +1374,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
 // a row repeat it, in parallel) and goes straight on to its grid points.  Removes the serial row-setup kernel
 // and the inter-kernel gap from the latency-critical single-profile call.
 template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_solo_kernel(const VfoParams p) {
+__global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_solo_kernel(const VfoParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockScratch sc;
   __shared__ ProfileRecord s_rec;
@@ -1435,7 +1435,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar) {
 }
 
 template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_fused_kernel(const VfoParams p, const int n_items) {
+__global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_fused_kernel(const VfoParams p, const int n_items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockScratch sc;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -1616,9 +1616,12 @@ cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64
   return literal ? launch_rowwarp_t<1, true>(p, n_ctas, stream) : launch_rowwarp_t<1, false>(p, n_ctas, stream);
 }
 
-int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm) {
-  const int by_smem = (int)((size_t)max_smem_per_sm / (vfo_tile_smem_bytes(n_alt) + 1024));
-  return by_smem < kTileMinBlocks ? (by_smem < 1 ? 1 : by_smem) : kTileMinBlocks;
+int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm, bool solo_kernel) {
+  const size_t a = sizeof(double) * 5 * (size_t)n_alt, b = vfo_tile_smem_bytes(n_alt);
+  const size_t per_cta = (solo_kernel && a > b) ? a : b;
+  const int by_smem = (int)((size_t)max_smem_per_sm / (per_cta + 1024));
+  const int by_regs = solo_kernel ? kSoloMinBlocks : kTileMinBlocks;
+  return by_smem < by_regs ? (by_smem < 1 ? 1 : by_smem) : by_regs;
 }
 
 template <int MODE, bool LITERAL>

@@ -12,10 +12,12 @@ constexpr int kMaxWarps = 8;
 #define PRHF_TILE_THREADS 256
 #endif
 #ifndef PRHF_TILE_MINB
-#define PRHF_TILE_MINB 3
+#define PRHF_TILE_MINB 4
 #endif
 constexpr int kTileThreads = PRHF_TILE_THREADS;   // K2 block size (multiple of 64, <= 256)
-constexpr int kTileMinBlocks = PRHF_TILE_MINB;    // K2 resident CTAs per SM the register budget targets
+constexpr int kTileMinBlocks = PRHF_TILE_MINB;    // K2 resident CTAs per SM the register budget targets (64 registers:
+                                                  // the grid loop itself does not spill, profiles/sweep_variants_r01c.log)
+constexpr int kSoloMinBlocks = 3;                 // the single-launch kernel carries the row setup as well: 80 registers
 constexpr int kRowsPerCta = kThreads / 32;   // K1: one warp per sounding frequency
 constexpr int kRowWarpMaxPoints = 4096;      // direct-mode calls with n_points up to this use the row-per-warp kernel
 constexpr int kMultPad = 4;                  // extra multiplier-table entries (value 1) past n_points
@@ -96,7 +98,7 @@ struct VfoParams {
 };
 
 size_t vfo_smem_bytes(int n_alt);
-int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm);
+int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm, bool solo_kernel);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
