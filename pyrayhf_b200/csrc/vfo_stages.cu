@@ -75,18 +75,62 @@ __global__ void smooth_grid_kernel(int n, double step, double start, double end,
 }
 
 // ---- lib:410-427: stretched altitudes, their spacings, and the profile sampled on them ----
-// grid = (chunks of points, frequency rows); the truncated altitude axis is staged in shared memory.
+// grid = (chunks of points, frequency rows).  The truncated profile is staged in shared memory together with the
+// per-level slopes (fp[j+1] - fp[j]) / (xp[j+1] - xp[j]): numpy forms exactly that quotient for every query, so
+// computing it once per level is bit-identical and takes three IEEE divisions per POINT out of the kernel, which
+// would otherwise make it division-bound instead of write-bound.
+struct RegridTable {
+  const double* alt;     // [nt]
+  const double* val[3];  // den, bmag, bpsi
+  const double* slope[3];
+};
+__device__ __forceinline__ double regrid_interp(double x, int j, const RegridTable& t, int q, int n) {
+  const double* fp = t.val[q];
+  if (n == 1) return fp[0];                                 // numpy's single-node branch has no NaN test
+  if (j == -2) return x;
+  if (j == -1) return fp[0];
+  if (j >= n - 1) return fp[n - 1];
+  const double x0 = t.alt[j], f0 = fp[j];
+  if (x0 == x) return f0;
+  const double slope = t.slope[q][j];
+  double r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, x0)), f0);
+  if (r != r) {                                             // numpy's NaN rescue
+    const double f1 = fp[j + 1];
+    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, t.alt[j + 1])), f1);
+    if (r != r && f0 == f1) r = f0;
+  }
+  return r;
+}
 __global__ void __launch_bounds__(kStageThreads) regrid_write_kernel(const RegridParams p) {
-  extern __shared__ double s_alt[];
+  extern __shared__ double s_tab[];
   const int nt = p.rec->nt;
-  for (int k = threadIdx.x; k < nt; k += blockDim.x) s_alt[k] = p.alt[k];
-  __syncthreads();
   if (nt < 1) return;
+  RegridTable t;
+  double* w = s_tab;
+  t.alt = w;
+  for (int k = threadIdx.x; k < nt; k += blockDim.x) w[k] = p.alt[k];
+  w += nt;
+  const double* src[3] = {p.den, p.bmag, p.bpsi};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double* v = w;
+    double* sl = w + nt;
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+      const double f0 = src[q][k];
+      v[k] = f0;
+      if (k + 1 < nt) sl[k] = __ddiv_rn(__dsub_rn(src[q][k + 1], f0), __dsub_rn(p.alt[k + 1], p.alt[k]));
+    }
+    t.val[q] = v;
+    t.slope[q] = sl;
+    w += 2 * nt;
+  }
+  __syncthreads();
   const int r = blockIdx.y;
-  const double alt0 = s_alt[0];
+  const double alt0 = t.alt[0];
   const double span = __dsub_rn(p.row_hc[r], alt0);         // lib:413 (NaN on rows that never reflect)
   const int n = p.n_points;
   const int64_t base = (int64_t)r * n;
+  const double inv_step = (nt > 1) ? (double)(nt - 1) / (t.alt[nt - 1] - alt0) : 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double h = __dadd_rn(__dmul_rn(p.mult[i], span), alt0);
     if (p.alt_out) p.alt_out[base + i] = h;
@@ -94,10 +138,16 @@ __global__ void __launch_bounds__(kStageThreads) regrid_write_kernel(const Regri
       const double hn = __dadd_rn(__dmul_rn(p.mult[i + 1], span), alt0);
       p.dist_out[base + i] = (i + 1 < n) ? __dsub_rn(hn, h) : kBackoff;                   // lib:415-416
     }
-    const int j = np_bracket(h, s_alt, nt);
-    if (p.den_out) p.den_out[base + i] = np_interp_at(h, j, s_alt, p.den, nt);          // lib:424-426
-    if (p.bmag_out) p.bmag_out[base + i] = np_interp_at(h, j, s_alt, p.bmag, nt);
-    if (p.bpsi_out) p.bpsi_out[base + i] = np_interp_at(h, j, s_alt, p.bpsi, nt);
+    // bracket: the uniform-grid guess when it verifies, else the binary search
+    int j;
+    {
+      const int g = min(max(__double2int_rd((h - alt0) * inv_step), 0), nt - 1);
+      if (h == h && t.alt[g] <= h && (g == nt - 1 ? h <= t.alt[g] : h < t.alt[g + 1])) j = g;
+      else j = np_bracket(h, t.alt, nt);
+    }
+    if (p.den_out) p.den_out[base + i] = regrid_interp(h, j, t, 0, nt);                 // lib:424-426
+    if (p.bmag_out) p.bmag_out[base + i] = regrid_interp(h, j, t, 1, nt);
+    if (p.bpsi_out) p.bpsi_out[base + i] = regrid_interp(h, j, t, 2, nt);
   }
 }
 
@@ -238,14 +288,18 @@ cudaError_t launch_smooth_grid(double start, double end, int n_points, double sh
 
 cudaError_t launch_regrid_write(const RegridParams& p, int n_alt, cudaStream_t stream) {
   if (p.n_freq <= 0 || p.n_points <= 0) return cudaSuccess;
-  const size_t smem = sizeof(double) * (size_t)n_alt;
+  const size_t smem = sizeof(double) * 7 * (size_t)n_alt;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute((const void*)regrid_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
   }
-  // enough CTAs per row to cover the GPU a few times over; every thread then strides over its points
-  int chunks = (p.n_points + kStageThreads * 4 - 1) / (kStageThreads * 4);
+  // every CTA builds the slope table once (a few divisions per thread), so give it at least 16 points per thread,
+  // unless that would leave fewer than ~4 CTAs per SM
+  int per_thread = 16;
+  while (per_thread > 2 && (int64_t)p.n_freq * ((p.n_points + kStageThreads * per_thread - 1) / (kStageThreads * per_thread)) < 148 * 4)
+    per_thread >>= 1;
+  int chunks = (p.n_points + kStageThreads * per_thread - 1) / (kStageThreads * per_thread);
   if (chunks < 1) chunks = 1;
   if (p.n_freq > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)chunks, (unsigned)p.n_freq);
