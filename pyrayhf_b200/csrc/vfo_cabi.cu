@@ -53,9 +53,8 @@ struct prhf_ctx {
   long long* trace = nullptr;        // developer phase trace buffer (PRHF_TRACE builds)
   size_t trace_k1_off = 0;           // K1 entries start here (in long longs)
   // planned mode (small batches): tile plan, compact tile list, K1 completion counter
-  unsigned* live_count = nullptr;    // [0] live-row counter of planned mode, [2..3] the fused kernel's barrier words,
+  unsigned* live_count = nullptr;    // [0] live-row counter of planned mode,
                                      // [4..5] 8-byte scratch word of prhf_find_vh_f64
-  bool use_fused = false;            // PRHF_FUSED=1: planned mode as one cooperative launch (no faster, kept for study)
   bool use_solo = true;              // PRHF_NO_SOLO=1: single-profile calls through the two-kernel planned mode
   bool use_pdl = true;               // PRHF_NO_PDL=1: plain stream order between K1 and K2
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
@@ -281,7 +280,6 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   ctx->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if (const char* s = getenv("PRHF_PLANNED_MAX_ROWS")) ctx->planned_max_rows = atoi(s);
   if (const char* s = getenv("PRHF_NO_GRAPH")) ctx->use_graphs = (atoi(s) == 0);
-  if (const char* s = getenv("PRHF_FUSED")) ctx->use_fused = (atoi(s) != 0);
   if (const char* s = getenv("PRHF_NO_PDL")) ctx->use_pdl = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_SOLO")) ctx->use_solo = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
@@ -478,11 +476,9 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
       PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, sizeof(unsigned), stream));
       P.live_count = ctx->live_count;
       P.live_list = ctx->live_list;
-      P.grid_bar = ctx->live_count + 2;
     } else {
       P.live_count = nullptr;
       P.live_list = nullptr;
-      P.grid_bar = nullptr;
     }
     P.rows_in_launch = np * n_freq;
     P.use_pdl = ctx->use_pdl ? 1 : 0;
@@ -508,18 +504,6 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
         ctx->timed_pairs++;
       }
       continue;
-    }
-    if (planned && ctx->use_fused && !ctx->kernel_timing) {
-      // one cooperative launch: row setup, grid barrier, tiles
-      const int rows_per_cta = prhf::kRowsPerCta * rows_per_warp;
-      const int64_t n_items = np * ((n_freq + rows_per_cta - 1) / rows_per_cta);
-      cudaError_t fe = prhf::launch_vfo_fused(P, mode, literal, (int)n_items, 1 << 20, ctx->sm_count, stream);
-      if (fe == cudaSuccess) {
-        ctx->launches += 1;
-        continue;
-      }
-      cudaGetLastError();
-      ctx->use_fused = false;                                 // e.g. cooperative launch unsupported: two launches
     }
     // direct mode with few grid points per row: row-per-warp kernel (profile staged once per CTA)
     const bool rowwarp = !planned && n_seg == 1 && n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp;

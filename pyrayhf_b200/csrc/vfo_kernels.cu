@@ -1114,7 +1114,7 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
   }
 }
 
-// ProfileRecord through L2 (ld.cg): in the fused kernel it was written by another CTA of the same launch.
+// ProfileRecord through L2 (ld.cg): written by the row-setup grid, which may still be draining under PDL.
 __device__ __forceinline__ ProfileRecord load_profile_record(const ProfileRecord* ptr) {
   union { ProfileRecord r; int4 v[4]; } u;
   const int4* src = reinterpret_cast<const int4*>(ptr);
@@ -1411,43 +1411,8 @@ __global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_solo_kernel(
   tile_body<MODE, LITERAL>(p, lrow, span, &s_rec, (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
 }
 
-// Fused form of the planned mode (small batches), launched cooperatively with one wave of CTAs: the row
-// setup (K1) and the tiles (K2) run in ONE kernel separated by a grid-wide barrier, which removes the
-// second launch and the inter-kernel drain/fill from the latency-critical single-profile path.
-// The barrier is sense-reversing on two words in global memory (arrive count, generation): it resets
-// itself, so the same captured graph can replay the launch.
-__device__ __forceinline__ void grid_barrier(unsigned* bar) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned* vgen = bar + 1;
-    const unsigned gen = *vgen;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-      bar[0] = 0u;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*vgen == gen) __nanosleep(32);
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-template <int MODE, bool LITERAL>
-__global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_fused_kernel(const VfoParams p, const int n_items) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ BlockScratch sc;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    rows_body(p, MODE, item, reinterpret_cast<double*>(smem_raw), sc, nullptr, nullptr);
-    __syncthreads();
-  }
-  grid_barrier(p.grid_bar);
-  planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
-}
-
 // ------------------------------------------------------------------------------------------
-// elementwise mu / mu' (lib:161-256) for callers outside the fused path
+// elementwise mu / mu' (lib:161-256) for callers outside the fused operator
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool LITERAL, bool ISO>
 __global__ void mu_mup_kernel(const double* __restrict__ X, const double* __restrict__ Y,
@@ -1653,26 +1618,6 @@ cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t
 }
 
 template <int MODE, bool LITERAL>
-static cudaError_t launch_fused_t(const VfoParams& p, int n_items, int max_grid, int sm_count, cudaStream_t stream) {
-  static_assert(kTileThreads == kThreads, "the fused kernel runs the row setup with the tile kernel's block size");
-  const size_t smem = vfo_smem_bytes(p.n_alt);
-  auto kern = vfo_fused_kernel<MODE, LITERAL>;
-  cudaError_t e = grant_dynamic_smem((const void*)kern, 5 + MODE * 2 + (LITERAL ? 1 : 0), smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
-  if (e != cudaSuccess) return e;
-  int grid = per_sm * sm_count;
-  if (grid > max_grid) grid = max_grid;
-  if (grid < 1) return cudaErrorCooperativeLaunchTooLarge;
-  VfoParams pc = p;
-  pc.slots = grid;                                        // the planner sizes tiles for the CTAs that exist
-  int items = n_items;
-  void* args[] = {(void*)&pc, (void*)&items};
-  return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kTileThreads), args, smem, stream);
-}
-
-template <int MODE, bool LITERAL>
 static cudaError_t launch_solo_t(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
   static_assert(kTileThreads == kThreads, "the solo kernel runs the row setup with the tile kernel's block size");
   const size_t a = sizeof(double) * 5 * (size_t)p.n_alt, b = vfo_tile_smem_bytes(p.n_alt);
@@ -1688,15 +1633,6 @@ cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t 
   if (mode == 0)
     return literal ? launch_solo_t<0, true>(p, n_tiles, stream) : launch_solo_t<0, false>(p, n_tiles, stream);
   return literal ? launch_solo_t<1, true>(p, n_tiles, stream) : launch_solo_t<1, false>(p, n_tiles, stream);
-}
-
-cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
-                             cudaStream_t stream) {
-  if (mode == 0)
-    return literal ? launch_fused_t<0, true>(p, n_items, max_grid, sm_count, stream)
-                   : launch_fused_t<0, false>(p, n_items, max_grid, sm_count, stream);
-  return literal ? launch_fused_t<1, true>(p, n_items, max_grid, sm_count, stream)
-                 : launch_fused_t<1, false>(p, n_items, max_grid, sm_count, stream);
 }
 
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream) {

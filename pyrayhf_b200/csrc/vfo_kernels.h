@@ -81,7 +81,6 @@ struct VfoParams {
   LiveRow* live_list;          // [rows_in_launch]
   int64_t rows_in_launch;
   int use_pdl;                 // launch the tile kernel with programmatic stream serialization
-  unsigned* grid_bar;          // fused kernel: {arrive count, generation}, both self-maintaining
   int max_seg;             // stride of `partial` per row; planner's upper bound on n_seg
   int slots;               // resident tile-kernel CTAs on the device
   int n_sm, ctas_per_sm;   // its factors
@@ -103,8 +102,6 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
 cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
-cudaError_t launch_vfo_fused(const VfoParams& p, int mode, bool literal, int n_items, int max_grid, int sm_count,
-                             cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
