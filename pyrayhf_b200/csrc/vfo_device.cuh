@@ -140,11 +140,16 @@ __device__ __forceinline__ double ah_fast(double X, double Y, double sn, double 
     YdDdY = fma(a2, rb, beta) - 2.0 * a;
   }
   const double rmu = rsqrt_fast(u);
-  const double mu = u * rmu;
+  const double mu = fmin(u * rmu, 1.0);
   const double br = fma(0.5 * q, YdDdY, X * fma(q, dDdX, fma(2.0, X, -1.0)));
   double mup = fma(-(invD * rmu), br, mu);
-  if (!(u >= 0.0 && u <= 1.0)) mup = CUDART_NAN;     // lib:233 and lib:238
-  if (mu_out) *mu_out = (u >= 0.0 && u <= 1.0) ? mu : CUDART_NAN;
+  // lib:233: u < 0 -> NaN.  lib:238: mu > 1 -> NaN, where the reference's mu is sqrt(fl(1 - q)): that exceeds 1
+  // exactly when fl(1 - q) >= 1 + 2^-51 (the square root of 1 + 2^-52 rounds back to 1).  The same rounding is
+  // applied to q here, so that vacuum (q == 0, kept) and the faintest plasma below the gyrofrequency in X-mode
+  // (q = -1e-15, dropped) come out as in the reference; u itself carries a reciprocal's rounding in O-mode.
+  const bool ok = (u >= 0.0) && ((1.0 - q) <= 1.0000000000000002);
+  if (!ok) mup = CUDART_NAN;
+  if (mu_out) *mu_out = ok ? mu : CUDART_NAN;
   return mup;
 }
 
@@ -155,11 +160,11 @@ __device__ __forceinline__ double ah_fast(double X, double Y, double sn, double 
 //   O-mode:  N = Xm1 P + w, G = P + w, mu^2 = N/G, rs = 1/sqrt(Xm1^2 N G):  mu = Xm1 N rs,
 //            1/G = (Xm1 N rs)(Xm1 rs), q = X P / G, 1/(D mu) = P rs   -- assumes Xm1 > 0, which holds at
 //            every grid point below the X = 1 reflection level (rows that start above it take ah_fast)
-// Inputs: YTh = Y sin(psi) / sqrt(2) (so that a = YTh^2), YL = Y cos(psi).  Returns mu' and mu; the caller
-// tests validity (mu <= 1, not NaN) on the bit patterns with integer instructions, keeping compares off the
+// Inputs: YTh = Y sin(psi) / sqrt(2) (so that a = YTh^2), YL = Y cos(psi).  Returns mu', mu and q = X (1-X) / D; the
+// caller tests validity (keep_term) on the bit patterns with integer instructions, keeping compares off the
 // FP64 pipe.  36 (X) / 37 (O) FP64 instructions.
 template <int MODE>
-__device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double* mu_out) {
+__device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double* mu_out, double* q_out) {
   const double Xm1 = 1.0 - X;
   const double a = YTh * YTh;
   const double w = (YL * YL) * Xm1;
@@ -195,15 +200,27 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
   }
   const double br = fma(q, hYd, X * fma(q, dDdX, fma(2.0, X, -1.0)));
   *mu_out = mu;
+  *q_out = q;
   return fma(-c, br, mu);
 }
 
 // mu' is kept when the reference keeps it: mu not NaN (lib:233), mu <= 1 (lib:238), mu' itself not NaN
-// (nansum, lib:288).  Integer tests on the IEEE bit patterns (mu >= 0 by construction).
-__device__ __forceinline__ bool keep_term(double mu, double mup) {
-  const unsigned long long mb = (unsigned long long)__double_as_longlong(mu);
-  const unsigned long long pb = (unsigned long long)__double_as_longlong(mup) & 0x7fffffffffffffffULL;
-  return (mb <= 0x3ff0000000000000ULL) && (pb <= 0x7ff0000000000000ULL);
+// (nansum, lib:288).  Integer tests on the IEEE bit patterns.
+// lib:238 is decided on q = X (1-X) / D rather than on mu: the reference's mu is sqrt(fl(1 - q)), which exceeds 1
+// exactly when q <= -3 * 2^-53 (fl(1 - q) >= 1 + 2^-51; the square root of 1 + 2^-52 rounds back to 1).  The mu
+// computed here comes out of a reciprocal square root and is only good to 3e-16, which is not enough to tell
+// vacuum (q == 0: kept, e.g. zero density below the layer) from the faintest plasma below the gyrofrequency in
+// X-mode (q = -1e-15: dropped).  Both cases were found by tests/test_gpu_fuzz.py.
+// As unsigned integers the doubles order as: +0 ... +inf, NaN, -0 ... -inf, and both thresholds have a zero low
+// word, so each test is ONE 32-bit compare on the high word:
+//   q > -3 * 2^-53          <=>  hi(q)  < 0xBCA80000
+//   mu' finite               <=>  hi(|mu'|) < 0x7FF00000
+// A NaN mu (lib:233: D E < 0 under the reciprocal square root) makes mu' NaN, so mu needs no test of its own; an
+// infinite mu' cannot come out of ah_hot (mu == 0 gives 0 * inf = NaN there).
+__device__ __forceinline__ bool keep_term(double mup, double q) {
+  const unsigned ph = (unsigned)__double2hiint(mup) & 0x7fffffffu;
+  const unsigned qh = (unsigned)__double2hiint(q);
+  return (ph < 0x7ff00000u) && (qh < 0xBCA80000u);
 }
 
 // sin/cos of (r_k + delta) from the node's sin/cos and a short Taylor series in delta (|delta| <= 0.05:

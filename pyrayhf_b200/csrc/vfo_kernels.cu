@@ -425,7 +425,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     if (d < 0.0) chk |= 1;
     // finite <=> (x - x) == 0
     if (!(((d - d) + (b - b)) + ((ps - ps) + (a - a)) == 0.0)) chk |= 2;
-    bmax = fmax(bmax, fabs(b));
+    if (p.n_points > 1 || k == 0) bmax = fmax(bmax, fabs(b));   // n_points == 1: the only grid point is level 0
     if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 2e-15 * fmax(fabs(a), mean_step))) chk |= 4;   // ~8 ulp
     if (!(a > 0.0)) chk |= 2;                           // the fast paths compare altitudes as integers
     if (k + 1 < nt) {
@@ -919,7 +919,8 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
 // ROWSCALE: the staged nodes are shared by several rows (row-per-warp kernel) and hold density / field
 // un-multiplied; the row's cp^2/f^2 and g_p/f are applied here (two more FP64 multiplies per point).
 template <int MODE, int PATH, bool ROWSCALE>
-__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out) {
+__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out,
+                                             double* q_out) {
   const Node& nd = nodes[j - rc.jlo];
   const double t = h - nd.alt;
   double X = fma(nd.sx, t, nd.x);
@@ -928,14 +929,14 @@ __device__ __forceinline__ double fast_point(double h, int j, const Node* nodes,
     // node fields: y = Y sin(psi)/sqrt(2), sy its slope; srad = Y cos(psi), sn = its slope
     double yth = fma(nd.sy, t, nd.y), yl = fma(nd.sn, t, nd.srad);
     if (ROWSCALE) { yth *= rc.ky; yl *= rc.ky; }
-    return ah_hot<MODE>(X, yth, yl, mu_out);
+    return ah_hot<MODE>(X, yth, yl, mu_out, q_out);
   }
   double Y = fma(nd.sy, t, nd.y);
   if (ROWSCALE) Y *= rc.ky;
   double sn, cs;
   if (PATH == kPathFastS) rotate_sincos_small(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
   else rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
-  return ah_hot<MODE>(X, (Y * sn) * 0.70710678118654752, Y * cs, mu_out);
+  return ah_hot<MODE>(X, (Y * sn) * 0.70710678118654752, Y * cs, mu_out, q_out);
 }
 
 // Bracket for altitude grids K1 flagged uniform (every level within ~8 ulp of alt0 + k * mean step, e.g. any
@@ -988,11 +989,11 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
       j0 = find_bracket_pos(h0, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
       j1 = find_bracket_pos(h1, nodes, rc.jlo, rc.jhi, j0);
     }
-    double mu0, mu1;
-    const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0);
-    const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1);
-    acc0 = fma(keep_term(mu0, p0) ? p0 : 0.0, dh0, acc0);            // nansum (lib:288)
-    acc1 = fma((keep_term(mu1, p1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
+    double mu0, mu1, q0, q1;
+    const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0, &q0);
+    const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1, &q1);
+    acc0 = fma(keep_term(p0, q0) ? p0 : 0.0, dh0, acc0);        // nansum (lib:288)
+    acc1 = fma((keep_term(p1, q1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
   }
   // lib:416: the row's last grid point weighs 1e-6.  The table is padded with copies of its last entry, so that
   // point entered the loop with weight 0; its owner adds the term here instead of two selects per iteration.
@@ -1002,9 +1003,9 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
     const double hl = fma(ml, rc.span, rc.alt0);
     const int g = __double2int_rd(ml * c1);
     const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, g) : find_bracket_pos(hl, nodes, rc.jlo, rc.jhi, g);
-    double mul;
-    const double pl = fast_point<MODE, PATH, ROWSCALE>(hl, jl, nodes, rc, &mul);
-    acc0 = fma(keep_term(mul, pl) ? pl : 0.0, kBackoff, acc0);
+    double mul, ql;
+    const double pl = fast_point<MODE, PATH, ROWSCALE>(hl, jl, nodes, rc, &mul, &ql);
+    acc0 = fma(keep_term(pl, ql) ? pl : 0.0, kBackoff, acc0);
   }
   return acc0 + acc1;
 }

@@ -1,0 +1,120 @@
+"""GPU: randomised profiles against the scalar C oracle (oracle/vfo_oracle_scalar.c).
+
+The goldens cover the reference's fixtures and smooth synthetic profiles; this test throws irregular inputs at every
+evaluation path of the kernels: noisy multi-layer densities with valleys, exact / nearly exact / roughly uniform /
+geometric altitude grids (the bracket of the grid loop is unverified on exactly uniform grids, verified otherwise),
+constant, slowly varying and jumping field angles, zero fields, tiny and large grids.  Acceptance as everywhere
+(conftest.assert_parity): NaN masks identical to the literal float64 restatement, X-mode <= 1e-9 against it, O-mode
+<= 1e-9 against the long-double truth and inside the literal restatement's rounding ball.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity
+from oracle import scalar, vfo_oracle
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter("ignore")
+CP = 8.97866275
+
+
+def chapman(alt, nm, hm, h):
+    z = (alt - hm) / h
+    return nm * np.exp(0.5 * (1.0 - z - np.exp(-z)))
+
+
+def random_profile(rng, kind):
+    n_alt = int(rng.integers(2, 400))
+    lo, hi = rng.uniform(60.0, 120.0), rng.uniform(400.0, 900.0)
+    grid = kind % 5
+    if grid == 0:
+        alt = lo + np.arange(n_alt) * float(rng.integers(1, 4))                  # exactly uniform
+    elif grid == 1:
+        alt = np.linspace(lo, hi, n_alt)                                          # uniform to an ulp
+    elif grid == 2:
+        alt = np.linspace(lo, hi, n_alt) * (1.0 + 1e-13 * rng.standard_normal(n_alt))   # just off uniform
+    elif grid == 3:
+        step = (hi - lo) / max(n_alt - 1, 1)
+        alt = np.linspace(lo, hi, n_alt) + 0.2 * step * rng.uniform(-1, 1, n_alt)        # roughly uniform
+    else:
+        alt = lo * (hi / lo) ** np.linspace(0.0, 1.0, n_alt)                      # geometric
+    alt = np.sort(alt)
+    fof2 = rng.uniform(2.0, 14.0)
+    den = chapman(alt, (fof2 * 1e6 / CP) ** 2, rng.uniform(200.0, 400.0), rng.uniform(25.0, 70.0))
+    for _ in range(int(rng.integers(0, 3))):
+        den = den + chapman(alt, (rng.uniform(0.5, 5.0) * 1e6 / CP) ** 2, rng.uniform(90.0, 220.0), rng.uniform(5.0, 25.0))
+    den = den * np.exp(rng.uniform(0.0, 0.2) * rng.standard_normal(n_alt))        # wiggles and valleys
+    if kind % 7 == 0:
+        den[: int(rng.integers(0, max(n_alt // 4, 1)))] = 0.0
+    bmag = 3.1e-5 * (6371.0 / (6371.0 + alt)) ** 3 * rng.uniform(1.0, 2.0)
+    if kind % 11 == 0:
+        bmag = np.zeros(n_alt)                                                     # unmagnetised branch
+    elif kind % 13 == 0:
+        bmag[rng.integers(0, n_alt, size=2)] = 0.0
+    ang = kind % 3
+    if ang == 0:
+        bpsi = np.full(n_alt, rng.uniform(0.0, 90.0))
+    elif ang == 1:
+        bpsi = rng.uniform(5.0, 85.0) + np.cumsum(rng.uniform(-0.02, 0.02, n_alt))
+    else:
+        bpsi = np.clip(rng.uniform(5.0, 85.0) + np.cumsum(rng.uniform(-4.0, 4.0, n_alt)), 0.0, 180.0)
+    freq = np.sort(np.concatenate((rng.uniform(0.05, 1.4 * fof2, 36), [0.9 * fof2, fof2, 1.01 * fof2, 30.0])))
+    return freq, den, bmag, bpsi, alt
+
+
+@pytest.fixture(scope="module")
+def vfo():
+    import torch
+    assert torch.cuda.is_available()
+    import pyrayhf_b200
+    return pyrayhf_b200
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_profiles(vfo, seed):
+    rng = np.random.default_rng(9000 + seed)
+    worst = {'O': 0.0, 'X': 0.0}
+    for kind in range(seed * 40, seed * 40 + 40):
+        freq, den, bmag, bpsi, alt = random_profile(rng, kind)
+        n = int(rng.choice([1, 2, 3, 50, 333, 2049, 4097]))
+        for mode in 'OX':
+            try:
+                lit = scalar.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n, variant=0,
+                                                       multiplier=vfo_oracle.stretch_multiplier(n))
+            except (ValueError, IndexError) as exc:
+                with pytest.raises(type(exc)):
+                    vfo.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n)
+                continue
+            tru = scalar.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n, variant=1,
+                                                   multiplier=vfo_oracle.stretch_multiplier(n))
+            got = vfo.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n)
+            assert_parity(got, lit, tru, mode, label="kind %d n %d mode %s" % (kind, n, mode))
+            m = np.isfinite(lit)
+            want = lit if mode == 'X' else tru
+            if m.any():
+                worst[mode] = max(worst[mode], float(np.max(np.abs(got[m] - want[m]) / np.abs(want[m]))))
+    print("seed", seed, "worst rel err", worst)
+
+
+def test_random_batch_equals_single_calls(vfo):
+    rng = np.random.default_rng(4242)
+    alt = np.linspace(80.0, 600.0, 261)
+    profs = []
+    for kind in range(24):
+        f, d, b, p, a = random_profile(rng, kind * 5 + 1)            # kind % 5 == 1: linspace grid, replaced below
+        profs.append((np.interp(alt, a, d), np.interp(alt, a, b), np.interp(alt, a, p)))
+    den, bmag, bpsi = (np.ascontiguousarray(np.stack(v)) for v in zip(*profs))
+    freq = np.arange(0.3, 15.0, 0.37)
+    for mode, n in (('X', 2500), ('O', 300)):
+        vb = vfo.vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode, n, errors='nan')
+        for q in range(den.shape[0]):
+            try:
+                one = vfo.vertical_forward_operator(freq, den[q], bmag[q], bpsi[q], alt, mode, n)
+            except (ValueError, IndexError):
+                assert np.all(np.isnan(vb[q]))
+                continue
+            assert np.array_equal(np.isnan(vb[q]), np.isnan(one))
+            m = np.isfinite(one)
+            assert np.allclose(vb[q][m], one[m], rtol=5e-10, atol=0)  # different kernels, same answers
