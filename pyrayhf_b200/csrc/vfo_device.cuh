@@ -149,7 +149,17 @@ __device__ __forceinline__ double ah_fast(double X, double Y, double sn, double 
   // (q = -1e-15, dropped) come out as in the reference; u itself carries a reciprocal's rounding in O-mode.
   const bool ok = (u >= 0.0) && ((1.0 - q) <= 1.0000000000000002);
   if (!ok) mup = CUDART_NAN;
-  if (mu_out) *mu_out = ok ? mu : CUDART_NAN;
+  if (mu_out) {
+    double mu_ret = ok ? mu : CUDART_NAN;
+    if (alpha == 0.0) {
+      // beta == 0 (a level without field, or Y_T == 0 at X == 1): the reference's derivative terms are 0/0, so
+      // mu' is NaN, but its mu = sqrt(1 - X (1-X) / (1-X)) is finite and the Snell tracers keep such a level
+      // (lib:229-238 with beta = 0).  The reciprocal square root above turned everything into NaN.
+      const double uz = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(X, Xm1), Xm1));
+      mu_ret = (uz >= 0.0 && uz <= 1.0) ? __dsqrt_rn(uz) : CUDART_NAN;
+    }
+    *mu_out = mu_ret;
+  }
   return mup;
 }
 

@@ -118,3 +118,96 @@ def test_random_batch_equals_single_calls(vfo):
             assert np.array_equal(np.isnan(vb[q]), np.isnan(one))
             m = np.isfinite(one)
             assert np.allclose(vb[q][m], one[m], rtol=5e-10, atol=0)  # different kernels, same answers
+
+
+def test_random_large_batch_against_oracle(vfo):
+    """200 irregular profiles on one altitude grid: the lane-per-row setup kernel with the row-per-warp kernel
+    (n_points = 64) and with the tile kernel (n_points = 2100), against the scalar oracle."""
+    rng = np.random.default_rng(777)
+    alt = 75.0 + 2.5 * np.arange(240)
+    rows = []
+    for kind in range(200):
+        f, d, b, p, a = random_profile(rng, 3 * kind + 1)
+        rows.append((np.interp(alt, a, d) * (1.0 + 0.05 * rng.standard_normal(alt.size)).clip(0.5, 1.5),
+                     np.interp(alt, a, b), np.interp(alt, a, p)))
+    den, bmag, bpsi = (np.ascontiguousarray(np.stack(v)) for v in zip(*rows))
+    den[5, :7] = 0.0                       # vacuum below the layer
+    den[9, 3] = -1.0                       # negative density below the peak: that profile fails (lib:94)
+    den[11] = den[11][::-1].copy()         # peak near the bottom
+    den[12, 0] = den[12].max() * 2.0       # peak at index 0: IndexError profile (lib:399)
+    freq = np.sort(rng.uniform(0.2, 16.0, 48))
+    for mode, n in (('X', 64), ('O', 64), ('X', 2100)):
+        got, st = vfo.vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode, n, errors='nan',
+                                                        return_status=True)
+        m = vfo_oracle.stretch_multiplier(n)
+        lit, st_o = scalar.vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode, n, variant=0, multiplier=m)
+        tru, _ = scalar.vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode, n, variant=1, multiplier=m)
+        assert np.array_equal(st, st_o) and st[9] == 1 and st[12] == 2
+        assert_parity(got, lit, tru, mode, label="batch %s %d" % (mode, n))
+
+
+def test_random_snell_rays_against_oracle():
+    """Irregular profiles for the Snell tracers: valleys put NaN islands (X > 1) between valid levels, so the
+    compaction, the crossing search across the gap and the apex interpolation on the full grid are exercised."""
+    from pyrayhf_b200 import snell
+    from oracle import snell_oracle
+    rng = np.random.default_rng(31337)
+    worst = 0.0
+    n_paths = 0
+    for kind in range(24):
+        _, den, bmag, bpsi, alt = random_profile(rng, 5 * kind + int(rng.integers(0, 5)))
+        if alt.size < 8:
+            continue
+        if kind % 3 == 0:
+            alt = alt - alt[0]                                      # ground level already present
+        f0 = rng.uniform(1.0e6, 14e6, 10)
+        el = rng.uniform(3.0, 90.0, 10)
+        mode = 'OX'[kind % 2]
+        for geo in ('cartesian', 'spherical'):
+            got = snell.trace_rays_snells_batched(f0, el, alt, den, bmag, bpsi, mode, geometry=geo, return_paths=True)
+            for i in range(f0.size):
+                o = snell_oracle.trace(f0[i], el[i], alt, den, bmag, bpsi, mode, geo)
+                if np.ndim(o['x']) == 0:
+                    assert got['n_path'][i] == 0 and np.isnan(got['group_path_km'][i]), (kind, geo, i)
+                    continue
+                n = int(got['n_path'][i])
+                assert n == o['x'].size, (kind, geo, i, n, o['x'].size)
+                n_paths += 1
+                assert np.allclose(got['z'][i, :n], o['z'], rtol=1e-12, atol=1e-12), (kind, geo, i)
+                assert np.allclose(got['x'][i, :n], o['x'], rtol=1e-8, atol=1e-8), (kind, geo, i)
+                for key in ('group_path_km', 'group_delay_sec', 'ground_range_km'):
+                    a, b = got[key][i], o[key]
+                    assert np.isnan(a) == np.isnan(b), (kind, geo, i, key)
+                    if not np.isnan(b):
+                        worst = max(worst, abs(a - b) / abs(b))
+                        assert abs(a - b) <= 1e-8 * abs(b), (kind, geo, i, key, a, b)
+                lo, hi = o['mid_candidates']
+                xm, zm = got['x_midpoint'][i], got['z_midpoint'][i]
+                ok = [abs(xm - o['x'][j]) <= 1e-7 * max(abs(o['x'][hi]), 1.0) and abs(zm - o['z'][j]) <= 1e-9 * max(o['z'][hi], 1.0)
+                      for j in (lo, hi)]
+                assert any(ok) or (np.isnan(xm) and np.isnan(o['x_midpoint'])), (kind, geo, i)
+    assert n_paths > 100
+    print("snell fuzz: %d rays with a path, worst relative error %.2e" % (n_paths, worst))
+
+
+def test_find_mu_mup_random_with_field_free_and_vacuum_elements(vfo):
+    rng = np.random.default_rng(99)
+    X = rng.uniform(0.0, 1.3, 4000)
+    Y = rng.uniform(0.0, 2.5, 4000)
+    psi = rng.uniform(0.0, 180.0, 4000)
+    X[::17] = 0.0                                   # vacuum: mu == 1 exactly in the reference
+    X[5::29] = 10.0 ** rng.uniform(-300, -14, X[5::29].size)   # faintest plasma: mu > 1 below the gyrofrequency (X-mode)
+    Y[3::23] = 0.0                                  # field-free elements inside a magnetised array: mu finite, mu' NaN
+    psi[7::31] = 0.0
+    psi[11::37] = 90.0
+    for mode in 'OX':
+        mu_r, mup_r = vfo_oracle.appleton_hartree(X, Y, psi, mode)
+        mu_g, mup_g = vfo.find_mu_mup(X, Y, psi, mode)
+        assert np.array_equal(np.isnan(mu_g), np.isnan(mu_r)), np.flatnonzero(np.isnan(mu_g) != np.isnan(mu_r))[:10]
+        m = np.isfinite(mu_r)
+        assert np.allclose(mu_g[m], mu_r[m], rtol=1e-9, atol=0)
+        # mu' : compare where the reference is well conditioned (its O-mode values near X = 1 are noise)
+        both = np.isfinite(mup_r) & np.isfinite(mup_g)
+        assert np.array_equal(np.isnan(mup_g), np.isnan(mup_r)) or (np.isnan(mup_g) != np.isnan(mup_r)).sum() <= 2
+        sel = both & (np.abs(1.0 - X) > 1e-3)
+        assert np.allclose(mup_g[sel], mup_r[sel], rtol=1e-7, atol=0)
