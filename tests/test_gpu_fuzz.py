@@ -211,3 +211,35 @@ def test_find_mu_mup_random_with_field_free_and_vacuum_elements(vfo):
         assert np.array_equal(np.isnan(mup_g), np.isnan(mup_r)) or (np.isnan(mup_g) != np.isnan(mup_r)).sum() <= 2
         sel = both & (np.abs(1.0 - X) > 1e-3)
         assert np.allclose(mup_g[sel], mup_r[sel], rtol=1e-7, atol=0)
+
+
+def test_regrid_stage_random_profiles(vfo):
+    rng = np.random.default_rng(2024)
+    n_checked = 0
+    for kind in range(30):
+        freq, den, bmag, bpsi, alt = random_profile(rng, kind)
+        f_hz = freq[::3] * 1e6
+        mode = 'OX'[kind % 2]
+        n = int(rng.choice([1, 2, 37, 400]))
+        try:
+            ref = vfo_oracle.regrid_dict(f_hz, den, bmag, bpsi, alt, mode, n)
+        except (ValueError, IndexError) as exc:
+            with pytest.raises(type(exc)):
+                vfo.regrid_to_nonuniform_grid(f_hz, den, bmag, bpsi, alt, mode=mode, n_points=n)
+            continue
+        got = vfo.regrid_to_nonuniform_grid(f_hz, den, bmag, bpsi, alt, mode=mode, n_points=n)
+        for key in ('alt', 'den', 'bmag', 'bpsi', 'crit_height', 'freq'):
+            a, b = np.asarray(got[key], float), np.asarray(ref[key], float)
+            assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)), (kind, key)
+            m = ~np.isnan(b)
+            if key in ('alt', 'crit_height', 'freq'):
+                assert np.allclose(a[m], b[m], rtol=1e-12, atol=0), (kind, key)
+            elif m.any():
+                # the altitudes differ from numpy's by an ulp (exp of the grid); in the steep Chapman tail, where a
+                # linear segment joins levels that are orders of magnitude apart, that moves the interpolant by far
+                # more than an ulp of its own value: compare against the scale of the profile
+                assert np.allclose(a[m], b[m], rtol=1e-9, atol=1e-13 * np.max(np.abs(b[m]))), (kind, key)
+        a, b = got['dist'], ref['dist']
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=1e-9, atol=1e-11)
+        n_checked += 1
+    assert n_checked >= 25
