@@ -243,3 +243,47 @@ def test_regrid_stage_random_profiles(vfo):
         assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(b)], b[~np.isnan(b)], rtol=1e-9, atol=1e-11)
         n_checked += 1
     assert n_checked >= 25
+
+
+def test_per_profile_altitude_grids_and_frequencies(vfo):
+    """Every profile of the batch on its OWN altitude grid (uniform, stretched, shifted) with its OWN frequencies:
+    row p must still equal the single-profile call on profile p (strided freq / alt inputs, numpy and torch)."""
+    import torch
+    rng = np.random.default_rng(606)
+    n_alt, n_freq, n_prof = 150, 30, 40
+    alts, dens, bms, pss, frs = [], [], [], [], []
+    for q in range(n_prof):
+        f, d, b, p, a = random_profile(rng, 5 * q + (q % 5))
+        lo, hi = a[0], a[-1]
+        grid = np.linspace(lo, hi, n_alt) if q % 2 == 0 else lo * (hi / lo) ** np.linspace(0.0, 1.0, n_alt)
+        alts.append(grid)
+        dens.append(np.interp(grid, a, d))
+        bms.append(np.interp(grid, a, b))
+        pss.append(np.interp(grid, a, p))
+        frs.append(np.sort(rng.uniform(0.3, 15.0, n_freq)))
+    alt, den, bmag, bpsi, freq = (np.ascontiguousarray(np.stack(v)) for v in (alts, dens, bms, pss, frs))
+    for mode, n in (('X', 300), ('O', 2200)):
+        got = vfo.vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode, n, errors='nan')
+        dev = torch.device('cuda', 0)
+        t = [torch.from_numpy(v).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+        got_t = vfo.vertical_forward_operator_batched(*t, mode, n, errors='nan').cpu().numpy()
+        assert np.array_equal(got, got_t, equal_nan=True)
+        for q in range(n_prof):
+            try:
+                one = vfo.vertical_forward_operator(freq[q], den[q], bmag[q], bpsi[q], alt[q], mode, n)
+            except (ValueError, IndexError):
+                assert np.all(np.isnan(got[q]))
+                continue
+            assert np.array_equal(np.isnan(got[q]), np.isnan(one)), q
+            m = np.isfinite(one)
+            assert np.allclose(got[q][m], one[m], rtol=5e-10, atol=0), q
+        # and three of them against the oracle
+        for q in (0, 1, 17):
+            try:
+                lit = scalar.vertical_forward_operator(freq[q], den[q], bmag[q], bpsi[q], alt[q], mode, n, variant=0,
+                                                       multiplier=vfo_oracle.stretch_multiplier(n))
+            except (ValueError, IndexError):
+                continue
+            tru = scalar.vertical_forward_operator(freq[q], den[q], bmag[q], bpsi[q], alt[q], mode, n, variant=1,
+                                                   multiplier=vfo_oracle.stretch_multiplier(n))
+            assert_parity(got[q], lit, tru, mode, label="profile %d" % q)
