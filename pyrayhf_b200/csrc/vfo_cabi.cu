@@ -625,6 +625,13 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     if (small && ctx->use_graphs) {
       const std::array<int64_t, 9> key = {n_freq, freq_shared, alt_shared, np, n_alt, mode, n_points, (int64_t)flags,
                                           ctx->seg_len_override};
+      if (ctx->graphs.size() >= 64 && ctx->graphs.find(key) == ctx->graphs.end()) {
+        // a caller cycling through many shapes: drop the cache rather than let it grow without bound
+        for (auto& kv : ctx->graphs)
+          for (int k = 0; k < 2; ++k)
+            if (kv.second.exec[k]) cudaGraphExecDestroy(kv.second.exec[k]);
+        ctx->graphs.clear();
+      }
       GraphEntry& ge = ctx->graphs[key];
       if (ge.epoch != ctx->epoch) {                           // buffers moved since capture: start over
         for (int k = 0; k < 2; ++k)

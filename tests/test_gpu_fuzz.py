@@ -287,3 +287,19 @@ def test_per_profile_altitude_grids_and_frequencies(vfo):
             tru = scalar.vertical_forward_operator(freq[q], den[q], bmag[q], bpsi[q], alt[q], mode, n, variant=1,
                                                    multiplier=vfo_oracle.stretch_multiplier(n))
             assert_parity(got[q], lit, tru, mode, label="profile %d" % q)
+
+
+def test_many_call_shapes_keep_results_stable(vfo):
+    """70 distinct call shapes, each called three times (the third call replays a captured CUDA graph; the graph
+    cache is bounded at 64 shapes and starts over beyond that): every repetition returns the same bits."""
+    from pyrayhf_b200 import synth
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    freq = synth.default_freq()[::4]
+    first = {}
+    for rep in range(3):
+        for n in range(30, 100):
+            vh = vfo.vertical_forward_operator(freq, den, bmag, bpsi, alt, 'X', n)
+            if rep == 0:
+                first[n] = vh
+            else:
+                assert np.array_equal(vh, first[n], equal_nan=True), (rep, n)
