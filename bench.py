@@ -100,7 +100,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -444,13 +444,34 @@ def run_b200_arm(args):
                 line["cpu_baseline"]["c_port_note"] = "unavailable: %s" % exc
             line["parity"] = {"rows_checked": int(ref_rows.size), "nan_mask_mismatches": mask_mismatch,
                               "max_rel_err_vs_numpy_port": relerr, "tolerance": 1e-9}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries (NCCL's version banner, for one) print to file descriptor 1.  The contract is ONE JSON line
+    on stdout, so everything written to fd 1 while the benchmark runs goes to stderr; `emit` writes the line to the
+    real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    text = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, text)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
