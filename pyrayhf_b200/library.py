@@ -192,7 +192,7 @@ def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_po
     return (vh, st) if return_status else vh
 
 
-def find_mu_mup(X, Y, bpsi, mode, *, y_tol=1e-12, literal=False):
+def find_mu_mup(X, Y, bpsi, mode, y_tol=1e-12, *, literal=False):
     """Phase / group refractive index on the GPU (library.py:161-256), numpy in/out."""
     X = np.asarray(X, dtype=float)
     Y = np.asarray(Y, dtype=float)

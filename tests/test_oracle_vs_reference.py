@@ -86,6 +86,37 @@ def test_install_rebinds_reference_global(ref):
     assert ref.vertical_forward_operator is original
 
 
+def test_install_stages_rebinds_every_stage_and_uninstall_restores(ref):
+    """install(stages=True) also swaps the standalone stage functions; uninstall() puts every original back."""
+    import pyrayhf_b200
+    names = ("vertical_forward_operator", "den2freq", "find_X", "find_Y", "smooth_nonuniform_grid",
+             "regrid_to_nonuniform_grid", "find_mu_mup", "find_vh")
+    originals = {n: getattr(ref, n) for n in names}
+    try:
+        pyrayhf_b200.install(stages=True)
+        for n in names:
+            assert getattr(ref, n) is getattr(pyrayhf_b200, n), n
+        # the reference's own callers resolve the names through the module globals
+        assert ref.find_vh.__module__.startswith("pyrayhf_b200")
+        assert ref.vertical_forward_operator.__globals__ is not ref.model_VH.__globals__
+        assert ref.model_VH.__globals__["find_X"] is pyrayhf_b200.find_X
+    finally:
+        pyrayhf_b200.uninstall()
+    for n in names:
+        assert getattr(ref, n) is originals[n], n
+    # the same signatures as the reference (positional names and defaults)
+    import inspect
+    for n in names + ("constants", "trace_ray_cartesian_snells"):
+        want = [(k, v.default) for k, v in inspect.signature(getattr(ref, n)).parameters.items()]
+        got = [(k, v.default) for k, v in inspect.signature(getattr(pyrayhf_b200, n)).parameters.items()
+               if v.kind is not inspect.Parameter.KEYWORD_ONLY]
+        assert got == want, (n, got, want)
+    # the spherical tracer's controls are keyword-only in the reference as well (lib:1468-1474)
+    want = [(k, v.default, v.kind) for k, v in inspect.signature(ref.trace_ray_spherical_snells).parameters.items()]
+    got = [(k, v.default, v.kind) for k, v in inspect.signature(pyrayhf_b200.trace_ray_spherical_snells).parameters.items()]
+    assert got == want, (got, want)
+
+
 def test_residual_tail_matches_reference_residual_VH(ref):
     """oracle.residual_from_model against the reference's residual_VH with model_VH patched to return a given
     curve (the reference's own tests patch the same module globals, tests/test_core.py:345-349)."""
