@@ -1251,21 +1251,20 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char* smem_raw, BlockScratch& sc) {
   const int live = (int)__ldcg(p.live_count);
-  // Cost model (SM cycles) for splitting every live row into ns segments of L points:
-  //   k = ceil(live * ns / n_sm) tiles land on the busiest SM; each costs L * cpp(resident CTAs) for its grid
-  //   points plus a fixed prologue/reduction overhead.  cpp: cycles per grid point of one SM with 1, 2, >= 3
-  //   resident tile CTAs (one CTA cannot hide the FP64 latency chain).  Constants fitted to the phase trace
-  //   (tools/trace_tiles.py) and the segment sweep in profiles/sweep_nseg_r01.log.
+  // How many segments per live row?  Measured (profiles/sweep_nseg_batch_r01.log, 2 ... 23 profiles): the step is
+  // shortest when the live tiles number about 1.3 x the resident CTA slots -- enough to even out where the hardware
+  // places the CTAs (under programmatic dependent launch they arrive while the row-setup grid still holds part of
+  // the SMs) -- as long as a tile keeps >= kPlanMinTilePoints grid points to amortise its prologue.  A cost model
+  // with per-SM tile counts was tried first and proved brittle: its ceil() steps flip the choice on a 5 % change of
+  // the live-row count.
   int n_seg = 1, seg_len = p.n_points;
   {
-    float best_cost = 3.0e38f;
-    const float inv_sm = 1.0f / (float)p.n_sm;
+    const float want = kPlanTilesPerSlot * (float)p.slots / (float)max(live, 1);
+    float best = 3.0e38f;
     for (int c = 0; c < p.n_cand; ++c) {
-      const float k = ceilf((float)max(live, 1) * (float)p.cand_seg[c] * inv_sm - 1e-4f);
-      const float resident = fminf(k, (float)p.ctas_per_sm);
-      const float cpp = (resident < 1.5f) ? kPlanCpp1 : ((resident < 2.5f) ? kPlanCpp2 : kPlanCpp3);
-      const float cost = k * ((float)p.cand_len[c] * cpp + kPlanTileOverhead);
-      if (cost < best_cost) { best_cost = cost; n_seg = p.cand_seg[c]; seg_len = p.cand_len[c]; }
+      if (p.cand_seg[c] > 1 && p.cand_len[c] < kPlanMinTilePoints) continue;
+      const float d = fabsf((float)p.cand_seg[c] - want);
+      if (d < best) { best = d; n_seg = p.cand_seg[c]; seg_len = p.cand_len[c]; }
     }
   }
   const int n_tiles = live * n_seg;

@@ -46,8 +46,8 @@ struct __align__(16) LiveRow {    // planned mode: one entry per row that reflec
 };
 // planner cost model (SM cycles): per-tile prologue + reduction, and loop cycles per grid point of one
 // tile when the SM is fully occupied (measured with the developer phase trace, tools/trace_tiles.py)
-constexpr float kPlanTileOverhead = 3500.0f;
-constexpr float kPlanCpp1 = 2.6f, kPlanCpp2 = 1.45f, kPlanCpp3 = 1.35f;
+constexpr float kPlanTilesPerSlot = 1.35f;        // planned mode: live tiles aimed at, per resident CTA slot
+constexpr int kPlanMinTilePoints = 5000;          // ... and the shortest tile worth its prologue
 constexpr int kMaxPlanCand = 32;
 
 struct VfoParams {
