@@ -199,6 +199,26 @@ def next_rows_section(torch, dev, stream, ctx, freq, den, bmag, bpsi, alt, with_
     out["regrid_stage"] = {"workload": "regrid_to_nonuniform_grid, %d freqs x %d points, 5 arrays written" % (n_freq, n_pts),
                            "ms": ms, "write_GBps": gbs, "frac_of_measured_hbm": gbs / hbm_peak,
                            "note": "row-setup kernel + write kernel; bound = HBM writes (MEASURED_PEAKS.json hbm_gbs)"}
+    # ---- elementwise stages on 16 Mi elements: find_X (1 read + 1 write), find_mu_mup (3 reads + 2 writes) ----
+    n_el = 1 << 24
+    ex = torch.rand(n_el, dtype=torch.float64, device=dev) * 0.9
+    ey = torch.rand(n_el, dtype=torch.float64, device=dev) * 0.5 + 0.05
+    ep = torch.rand(n_el, dtype=torch.float64, device=dev) * 90.0
+    eo1, eo2 = torch.empty_like(ex), torch.empty_like(ex)
+    fscal = torch.full((1,), 5e6, dtype=torch.float64, device=dev)
+    eden = ex * 1e11
+    ms = timed(lambda: ctx.check(L.prhf_find_x_f64(ctx.handle, vp(eden.data_ptr()), 1, vp(fscal.data_ptr()), 0, n_el,
+                                                   vp(eo1.data_ptr()), None, sp)))
+    gbs = 2 * n_el * 8 / (ms * 1e-3) / 1e9
+    out["find_X_stage"] = {"elements": n_el, "ms": ms, "GBps": gbs, "frac_of_measured_hbm": gbs / hbm_peak,
+                           "note": "bit-identical to numpy: one IEEE sqrt and one IEEE division per element keep it "
+                                   "FP64-bound (the fused operator uses reciprocal seeds instead)"}
+    ms = timed(lambda: ctx.check(L.prhf_mu_mup_f64(ctx.handle, vp(ex.data_ptr()), vp(ey.data_ptr()), vp(ep.data_ptr()),
+                                                   n_el, 1, 0, 0, vp(eo1.data_ptr()), vp(eo2.data_ptr()), sp)))
+    gbs = 5 * n_el * 8 / (ms * 1e-3) / 1e9
+    out["find_mu_mup_stage"] = {"elements": n_el, "ms": ms, "GBps": gbs, "frac_of_measured_hbm": gbs / hbm_peak,
+                                "note": "sincos + Appleton-Hartree per element: FP64-bound, not HBM-bound"}
+    del ex, ey, ep, eo1, eo2, eden
     # ---- Snell tracers: 174 frequencies x 64 elevations over the same profile ----
     elev = np.linspace(5.0, 88.0, 64)
     f_r = np.repeat(freq * 1e6, elev.size)

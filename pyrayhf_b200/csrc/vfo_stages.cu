@@ -35,6 +35,7 @@ inline unsigned stage_blocks(int64_t n, int per_thread = 1) {
 __global__ void den2freq_kernel(const double* __restrict__ den, int64_t n, double* __restrict__ out,
                                 int* __restrict__ negative_flag) {
   bool neg = false;
+#pragma unroll 4
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = den[i];
     neg |= (v < 0.0);
@@ -47,6 +48,7 @@ __global__ void den2freq_kernel(const double* __restrict__ den, int64_t n, doubl
 __global__ void find_x_kernel(const double* __restrict__ den, int64_t den_stride, const double* __restrict__ f_hz,
                               int64_t f_stride, int64_t n, double* __restrict__ X, int* __restrict__ negative_flag) {
   bool neg = false;
+#pragma unroll 4
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = den[i * den_stride];
     neg |= (v < 0.0);
@@ -58,6 +60,7 @@ __global__ void find_x_kernel(const double* __restrict__ den, int64_t den_stride
 // ---- lib:157: g_p * b / f ----
 __global__ void find_y_kernel(const double* __restrict__ f_hz, int64_t f_stride, const double* __restrict__ b,
                               int64_t b_stride, int64_t n, double* __restrict__ Y) {
+#pragma unroll 4
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     Y[i] = y_literal(b[i * b_stride], f_hz[i * f_stride]);
 }
