@@ -961,9 +961,11 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
   constexpr bool kAhead = !ROWSCALE;
   double2 mm_next = make_double2(1.0, 1.0);
   double mn_next = 1.0;
+  const double2* pm2 = m2 + ((i0 >> 1) + rc.lane0);                  // running pointers of the read-ahead
+  const double* pm1 = m + (i0 + 2 * rc.lane0 + 2);
   if (kAhead) {
     const int ip = i0 + 2 * rc.lane0;
-    if (ip < i1) { mm_next = __ldg(m2 + (ip >> 1)); mn_next = __ldg(m + ip + 2); }
+    if (ip < i1) { mm_next = __ldg(pm2); mn_next = __ldg(pm1); }
   }
   for (int i = i0 + 2 * rc.lane0; i < i1; i += 2 * rc.group) {
     double2 mm;
@@ -971,8 +973,9 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
     if (kAhead) {
       mm = mm_next;
       mn = mn_next;
-      const int in = i + 2 * rc.group;
-      if (in < i1) { mm_next = __ldg(m2 + (in >> 1)); mn_next = __ldg(m + in + 2); }
+      pm2 += rc.group;
+      pm1 += 2 * rc.group;
+      if (i + 2 * rc.group < i1) { mm_next = __ldg(pm2); mn_next = __ldg(pm1); }
     } else {
       mm = __ldg(m2 + (i >> 1));                                     // i0 is even, the table is padded
       mn = __ldg(m + i + 2);
@@ -993,7 +996,8 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
     const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0, &q0);
     const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1, &q1);
     acc0 = fma(keep_term(p0, q0) ? p0 : 0.0, dh0, acc0);        // nansum (lib:288)
-    acc1 = fma((keep_term(p1, q1) && i + 1 < i1) ? p1 : 0.0, dh1, acc1);
+    // (when n_points is odd the last pair's second point is a pad entry: h == h_c, weight h(pad) - h(pad) == 0)
+    acc1 = fma(keep_term(p1, q1) ? p1 : 0.0, dh1, acc1);
   }
   // lib:416: the row's last grid point weighs 1e-6.  The table is padded with copies of its last entry, so that
   // point entered the loop with weight 0; its owner adds the term here instead of two selects per iteration.
