@@ -77,6 +77,12 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
     else:
         raise ValueError("mode must be 'O' or 'X'")
     n_points = int(n_points)
+    if type(freq) is not np.ndarray:
+        # what `freq * 1e6` (library.py:491) and `f.size` (library.py:367) do to non-arrays in the reference
+        if isinstance(freq, (list, tuple)):
+            raise TypeError("can't multiply sequence by non-int of type 'float'")
+        if isinstance(freq, (int, float)) and not isinstance(freq, np.generic):
+            raise AttributeError("'float' object has no attribute 'size'")
     ctx = _cabi.context(device)
     st = _status_buf.get(ctx)
     if st is None:
@@ -93,8 +99,9 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
             return vh
         if rc > 0:
             ctx.check(rc)
-    if np.ndim(freq) > 1:
-        raise ValueError("operands could not be broadcast together: freq must be 0-d or 1-d")
+    if np.ndim(freq) > 1 and not (np.ndim(freq) == 2 and np.shape(freq)[0] == 1):
+        # the reference broadcasts freq against [n_alt, n_freq]: 0-d, 1-d and (1, F) work, anything else fails
+        raise ValueError("operands could not be broadcast together: freq must be 0-d, 1-d or of shape (1, F)")
     f, d, b, p, a = _vec(freq), _vec(den), _vec(bmag), _vec(bpsi), _vec(alt)
     n_alt = d.size
     if not (b.size == p.size == a.size == n_alt):

@@ -61,6 +61,11 @@ def test_no_cpu_fallback_without_gpu(lib):
     # argument errors that the reference raises before any arithmetic still surface
     with pytest.raises(ValueError, match="mode must be 'O' or 'X'"):
         pyrayhf_b200.vertical_forward_operator(np.array([2.0]), den, bmag, bpsi, alt, 'x', 50)
+    # the reference needs an ndarray for freq (freq * 1e6, f.size): lists and Python scalars fail the same way
+    with pytest.raises(TypeError, match="can't multiply sequence"):
+        pyrayhf_b200.vertical_forward_operator([2.0, 3.0], den, bmag, bpsi, alt, 'X', 50)
+    with pytest.raises(AttributeError, match="has no attribute 'size'"):
+        pyrayhf_b200.vertical_forward_operator(2.0, den, bmag, bpsi, alt, 'X', 50)
 
 
 def test_product_does_not_import_oracle():

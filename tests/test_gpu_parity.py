@@ -163,6 +163,18 @@ def test_error_behaviour(vfo):
     # 0-d frequency -> shape (1,)
     got = vfo.vertical_forward_operator(np.array(2.0), den, bmag, bpsi, alt, 'X', 100)
     assert got.shape == (1,)
+    # freq of shape (1, F) broadcasts in the reference and returns (F,); other 2-D / 3-D shapes fail there too
+    got2 = vfo.vertical_forward_operator(f[None, :], den, bmag, bpsi, alt, 'X', 100)
+    assert got2.shape == f.shape and np.array_equal(got2, vfo.vertical_forward_operator(f, den, bmag, bpsi, alt, 'X', 100),
+                                                    equal_nan=True)
+    for bad in (f[:, None], np.tile(f, (2, 1)), f[None, None, :]):
+        with pytest.raises(ValueError):
+            vfo.vertical_forward_operator(bad, den, bmag, bpsi, alt, 'X', 100)
+    with pytest.raises(TypeError):
+        vfo.vertical_forward_operator(list(f), den, bmag, bpsi, alt, 'X', 100)
+    with pytest.raises(AttributeError):
+        vfo.vertical_forward_operator(2.0, den, bmag, bpsi, alt, 'X', 100)
+    assert vfo.vertical_forward_operator(np.float64(2.0), den, bmag, bpsi, alt, 'X', 100).shape == (1,)
 
 
 @pytest.mark.parametrize("seg_len", [256, 1024, 4096, 100000])
