@@ -481,7 +481,12 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
       P.live_list = nullptr;
     }
     P.rows_in_launch = np * n_freq;
-    P.use_pdl = ctx->use_pdl ? 1 : 0;
+    // Programmatic dependent launch lets the tile grid start while the row-setup grid drains.  In planned mode that
+    // early start places the working CTAs on the SMs the row setup has already left and leaves the others short of
+    // tiles (profiles/trace of 4 profiles: 271 tiles on 64 SMs), which costs more than the overlap gains as soon as
+    // the row setup spans more than a couple of profiles (measured, 2 ... 23 profiles: better without from 3 on, up to
+    // 12 % at 12 profiles).
+    P.use_pdl = (ctx->use_pdl && !(planned && rows_total > 2 * (int64_t)n_freq)) ? 1 : 0;
     P.max_seg = n_seg;
     P.slots = slots;
     P.n_sm = ctx->sm_count;
