@@ -38,3 +38,4 @@ from pyrayhf_b200.snell import (  # noqa: E402,F401
     trace_ray_spherical_snells,
     trace_rays_snells_batched,
 )
+from pyrayhf_b200 import sharding  # noqa: E402,F401

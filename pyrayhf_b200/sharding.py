@@ -83,3 +83,51 @@ def vertical_forward_operator_sharded(freq, den, bmag, bpsi, alt, mode='O', n_po
                 else np.arange(*shard_bounds(n_prof, world, rk)))
         out[ridx] = parts[rk][:ridx.size].cpu().numpy()
     return out
+
+
+def _default_compute_single(freq, den, bmag, bpsi, alt, mode, n_points):
+    from pyrayhf_b200.library import vertical_forward_operator
+    return vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n_points)
+
+
+def vertical_forward_operator_sharded_by_frequency(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
+                                                   group=None, gather_to=0, compute=None):
+    """ONE profile, many sounding frequencies (BASELINE config 5: 1 740 of them): every frequency row is independent
+    (library.py:459-509 carries nothing from one row to the next), so rank r takes frequencies r, r + G, r + 2G, ...
+    -- interleaved, because rows above the critical frequency cost almost nothing and sit at the end of the sweep --
+    and the ``[F]`` result is assembled on rank ``gather_to`` (None: on every rank).  Errors of the reference
+    (negative density, peak at index 0) surface on every rank, as every rank sees the same profile.
+    """
+    import torch
+    import torch.distributed as dist
+    compute = compute or _default_compute_single
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    freq = np.ascontiguousarray(freq, dtype=np.float64).reshape(-1)
+    n_freq = freq.size
+    idx = interleaved_indices(n_freq, world, rank)
+    local = (np.asarray(compute(freq[idx], den, bmag, bpsi, alt, mode, n_points), dtype=np.float64)
+             if idx.size else np.empty(0))
+    if world == 1:
+        out = np.empty(n_freq)
+        out[idx] = local
+        return out
+    rows = -(-n_freq // world)
+    backend = dist.get_backend(group)
+    device = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    buf = torch.full((rows,), float('nan'), dtype=torch.float64, device=device)
+    if idx.size:
+        buf[:idx.size] = torch.from_numpy(local).to(device)
+    if gather_to is None or backend == 'nccl':
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)] if rank == gather_to else None
+        dist.gather(buf, parts, dst=gather_to, group=group)
+    if gather_to is not None and rank != gather_to:
+        return None
+    out = np.empty(n_freq)
+    for rk in range(world):
+        ridx = interleaved_indices(n_freq, world, rk)
+        out[ridx] = parts[rk][:ridx.size].cpu().numpy()
+    return out

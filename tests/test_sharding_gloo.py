@@ -63,6 +63,51 @@ def test_two_rank_sharding_matches_single_process(tmp_path, layout, n_prof):
     assert np.array_equal(got, want, equal_nan=True)
 
 
+def _oracle_compute_single(freq, den, bmag, bpsi, alt, mode, n_points):
+    from oracle import scalar, vfo_oracle
+    return scalar.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n_points, variant=0,
+                                            multiplier=vfo_oracle.stretch_multiplier(n_points))
+
+
+def _freq_worker(rank, world, port, n_freq, result_path):
+    sys.path.insert(0, ROOT)
+    warnings.simplefilter("ignore")
+    import torch.distributed as dist
+    from pyrayhf_b200 import sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        den, bmag, bpsi, alt = synth.single_day_profile()
+        freq = np.linspace(0.05, 9.0, n_freq)
+        out = sharding.vertical_forward_operator_sharded_by_frequency(freq, den, bmag, bpsi, alt, 'O', 80, gather_to=0,
+                                                                      compute=_oracle_compute_single)
+        if rank == 0:
+            np.save(result_path, out)
+        else:
+            assert out is None
+        out_all = sharding.vertical_forward_operator_sharded_by_frequency(freq, den, bmag, bpsi, alt, 'O', 80,
+                                                                          gather_to=None, compute=_oracle_compute_single)
+        assert out_all.shape == (n_freq,)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_freq", [37, 1])
+def test_two_rank_frequency_sharding_of_one_profile(tmp_path, n_freq):
+    """Config 5's shape: one profile, a long frequency sweep split over the ranks (interleaved), gathered on rank 0."""
+    import torch.multiprocessing as mp
+    from pyrayhf_b200 import synth
+    port = 31500 + (os.getpid() + n_freq) % 2000
+    path = str(tmp_path / "outf.npy")
+    mp.spawn(_freq_worker, args=(2, port, n_freq, path), nprocs=2, join=True)
+    got = np.load(path)
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    freq = np.linspace(0.05, 9.0, n_freq)
+    want = _oracle_compute_single(freq, den, bmag, bpsi, alt, 'O', 80)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
 def test_shard_bounds_cover_everything():
     from pyrayhf_b200 import sharding
     for n in (0, 1, 7, 8, 65341):
