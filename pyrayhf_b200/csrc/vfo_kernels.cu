@@ -777,6 +777,8 @@ struct RowConst {
   int lane0;        // index of this thread inside the group that shares the row (CTA: tid, warp: lane)
   int group;        // threads in that group (kTileThreads or 32)
   double kx, ky;    // cp^2/f^2 and g_p/f, applied per point when the staged nodes are not pre-scaled
+  const double* g_alt;   // the profile's raw altitude / density levels: O-mode points next to the reflection level
+  const double* g_den;   // re-evaluate X in numpy's operation order (near_reflection_tail)
 };
 
 // Bracket of h inside the staged window: last j in [jlo, jhi] with alt[j] <= h (jlo - 1 if below).
@@ -918,25 +920,54 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
 
 // ROWSCALE: the staged nodes are shared by several rows (row-per-warp kernel) and hold density / field
 // un-multiplied; the row's cp^2/f^2 and g_p/f are applied here (two more FP64 multiplies per point).
-template <int MODE, int PATH, bool ROWSCALE>
-__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out,
-                                             double* q_out) {
+// X and the two field terms of ah_hot at one grid point, from the staged levels.
+template <int PATH, bool ROWSCALE>
+__device__ __forceinline__ void fast_xy(double h, int j, const Node* nodes, const RowConst& rc, double* X_out,
+                                        double* yth_out, double* yl_out) {
   const Node& nd = nodes[j - rc.jlo];
   const double t = h - nd.alt;
   double X = fma(nd.sx, t, nd.x);
   if (ROWSCALE) X *= rc.kx;
+  *X_out = X;
   if (PATH == kPathFast0) {
     // node fields: y = Y sin(psi)/sqrt(2), sy its slope; srad = Y cos(psi), sn = its slope
     double yth = fma(nd.sy, t, nd.y), yl = fma(nd.sn, t, nd.srad);
     if (ROWSCALE) { yth *= rc.ky; yl *= rc.ky; }
-    return ah_hot<MODE>(X, yth, yl, mu_out, q_out);
+    *yth_out = yth;
+    *yl_out = yl;
+    return;
   }
   double Y = fma(nd.sy, t, nd.y);
   if (ROWSCALE) Y *= rc.ky;
   double sn, cs;
   if (PATH == kPathFastS) rotate_sincos_small(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
   else rotate_sincos(nd.sn, nd.cs, nd.srad * t, &sn, &cs);
-  return ah_hot<MODE>(X, (Y * sn) * 0.70710678118654752, Y * cs, mu_out, q_out);
+  *yth_out = (Y * sn) * 0.70710678118654752;
+  *yl_out = Y * cs;
+}
+
+// 0 < 1 - X < 1e-7, tested on the high word (0x3E7AD7F2 is the high word of 1e-7); see near_reflection_tail.
+__device__ __forceinline__ bool near_reflection(double X) { return (unsigned)__double2hiint(1.0 - X) < 0x3E7AD7F2u; }
+
+template <int MODE, int PATH, bool ROWSCALE>
+__device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out,
+                                             double* q_out, bool* near_out) {
+  double X, yth, yl;
+  fast_xy<PATH, ROWSCALE>(h, j, nodes, rc, &X, &yth, &yl);
+  *near_out = (MODE == 0) && near_reflection(X);
+  return ah_hot<MODE>(X, yth, yl, mu_out, q_out);
+}
+
+// X in the reference's own operation order: h = m * span + alt0 in two roundings (lib:413), np.interp on the raw levels
+// (lib:424), X = (sqrt(n) cp)^2 / f^2 (lib:136).
+__device__ __forceinline__ double literal_x(double mval, int j, const RowConst& rc) {
+  const double h = __dadd_rn(__dmul_rn(mval, rc.span), rc.alt0);
+  const double* xp = rc.g_alt;
+  const int n = rc.nt;
+  j = min(max(j, 0), n - 1);
+  while (j > 0 && h < xp[j]) --j;                         // the fast bracket may be one off next to a level
+  while (j + 1 < n && h >= xp[j + 1]) ++j;
+  return x_literal(np_interp_at(h, (h < xp[0]) ? -1 : j, xp, rc.g_den, n), rc.f_hz);
 }
 
 // Bracket for altitude grids K1 flagged uniform (every level within ~8 ulp of alt0 + k * mean step, e.g. any
@@ -948,10 +979,42 @@ __device__ __forceinline__ double fast_point(double h, int j, const Node* nodes,
 // take find_bracket_pos (guess, verify, binary search).
 __device__ __forceinline__ int bracket_uniform(int jlo, int jhi, int guess) { return min(max(guess, jlo), jhi); }
 
+// O-mode grid points with 1 - X < 1e-7 (the last few of a 20 000-point row).  mu' ~ (1 - X)^(-1/2) there and 1 - X
+// goes down to 1e-9 at the last point, so ONE ulp of X is worth up to 1e-7 of the term and, on steep profiles, more
+// than 1e-9 of the virtual height (conditioning; found by tools/fuzz_more.py).  The fast
+// interpolant (one FMA on pre-scaled levels, h from one FMA) is a few ulp from numpy's, so the hot loop leaves these
+// points out (one compare each) and this out-of-line pass adds them with X in the reference's own operation order.
+// Same thread, same stride and same weights as the hot loop; `first` is the first pair it skipped a point in.
+template <int PATH, bool UNIFORM, bool ROWSCALE>
+__device__ __noinline__ double near_reflection_tail(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                    int first, int i1, int n_points) {
+  const double c1 = rc.span * rc.inv_dalt;
+  double acc = 0.0;
+  for (int i = first; i < i1; i += 2 * rc.group) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = i + u;
+      const double mk = __ldg(m + k), mk1 = __ldg(m + k + 1);
+      const double h = fma(mk, rc.span, rc.alt0);
+      const double dh = fma(mk1, rc.span, rc.alt0) - h;
+      const int g = __double2int_rd(mk * c1);
+      const int j = UNIFORM ? min(max(g, rc.jlo), rc.jhi) : find_bracket_pos(h, nodes, rc.jlo, rc.jhi, g);
+      double X, yth, yl, mu, q;
+      fast_xy<PATH, ROWSCALE>(h, j, nodes, rc, &X, &yth, &yl);
+      if (!near_reflection(X) || k >= i1 || k == n_points - 1) continue;   // (the last point is added by the caller)
+      const double p = ah_hot<0>(literal_x(mk, j, rc), yth, yl, &mu, &q);
+      acc = fma(keep_term(p, q) ? p : 0.0, dh, acc);
+    }
+  }
+  return acc;
+}
+
 template <int MODE, int PATH, bool UNIFORM, bool ROWSCALE>
 __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
                                                 int i0, int i1, int n_points) {
   double acc0 = 0.0, acc1 = 0.0;
+  int first_near = 0x7fffffff;
+  const int il_row = n_points - 1;
   const double2* m2 = reinterpret_cast<const double2*>(m);
   const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
   // The tile kernels (long segments) read the multiplier table one iteration ahead, so that the L2 / L1 latency of
@@ -993,12 +1056,21 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
       j1 = find_bracket_pos(h1, nodes, rc.jlo, rc.jhi, j0);
     }
     double mu0, mu1, q0, q1;
-    const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0, &q0);
-    const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1, &q1);
-    acc0 = fma(keep_term(p0, q0) ? p0 : 0.0, dh0, acc0);        // nansum (lib:288)
+    bool near0, near1;
+    const double p0 = fast_point<MODE, PATH, ROWSCALE>(h0, j0, nodes, rc, &mu0, &q0, &near0);
+    const double p1 = fast_point<MODE, PATH, ROWSCALE>(h1, j1, nodes, rc, &mu1, &q1, &near1);
+    if (MODE == 0) {
+      // the row's very last point carries weight 0 in this loop and is evaluated after it: it must not trigger the tail
+      near0 = near0 && (i != il_row);
+      near1 = near1 && (i + 1 != il_row);
+      if (near0 || near1) first_near = min(first_near, i);   // left to near_reflection_tail
+    }
+    acc0 = fma((keep_term(p0, q0) && !near0) ? p0 : 0.0, dh0, acc0);        // nansum (lib:288)
     // (when n_points is odd the last pair's second point is a pad entry: h == h_c, weight h(pad) - h(pad) == 0)
-    acc1 = fma(keep_term(p1, q1) ? p1 : 0.0, dh1, acc1);
+    acc1 = fma((keep_term(p1, q1) && !near1) ? p1 : 0.0, dh1, acc1);
   }
+  if (MODE == 0 && first_near != 0x7fffffff)
+    acc0 += near_reflection_tail<PATH, UNIFORM, ROWSCALE>(nodes, rc, m, first_near, i1, n_points);
   // lib:416: the row's last grid point weighs 1e-6.  The table is padded with copies of its last entry, so that
   // point entered the loop with weight 0; its owner adds the term here instead of two selects per iteration.
   const int il = n_points - 1, ip = il & ~1;
@@ -1007,8 +1079,12 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
     const double hl = fma(ml, rc.span, rc.alt0);
     const int g = __double2int_rd(ml * c1);
     const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, g) : find_bracket_pos(hl, nodes, rc.jlo, rc.jhi, g);
-    double mul, ql;
-    const double pl = fast_point<MODE, PATH, ROWSCALE>(hl, jl, nodes, rc, &mul, &ql);
+    double Xl, ythl, yll, mul, ql;
+    fast_xy<PATH, ROWSCALE>(hl, jl, nodes, rc, &Xl, &ythl, &yll);
+    // (coarse grids: the last point is the only one this close, and with its weight of 1e-6 km an ulp of X is worth
+    //  < 1e-11 of the virtual height -- not worth an IEEE sqrt and two divisions on one lane of a 200-point row)
+    if (MODE == 0 && n_points >= 1024 && near_reflection(Xl)) Xl = literal_x(ml, jl, rc);
+    const double pl = ah_hot<MODE>(Xl, ythl, yll, &mul, &ql);
     acc0 = fma(keep_term(pl, ql) ? pl : 0.0, kBackoff, acc0);
   }
   return acc0 + acc1;
@@ -1171,6 +1247,8 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const double* g_alt = p.alt + prof * p.alt_stride;
 
   RowConst rc;
+  rc.g_alt = g_alt;
+  rc.g_den = g_den;
   rc.f_hz = __dmul_rn(f_mhz, 1e6);
   rc.alt0 = rec.alt0;
   rc.span = span;
@@ -1352,6 +1430,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
     const double span = p.row_span[lrow];
     if (!(span == span)) continue;
     RowConst rc;
+    rc.g_alt = g_alt;
+    rc.g_den = g_den;
     rc.f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);
     rc.alt0 = rec.alt0;
     rc.span = span;
