@@ -99,6 +99,34 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
                       int n_points, unsigned flags, double* vh_out, int* status);
 
 /*
+ * Same operator, pipelined, for LARGE batches whose buffers live wherever the caller has them (still
+ * library.py:459-509 per profile).  Every pointer may be a host pointer (page-locked memory recommended:
+ * cudaHostAlloc / cudaHostRegister / torch pin_memory; pageable memory works but copies serialise) or a device
+ * pointer, independently of the others; the library looks the pointer up (cudaPointerGetAttributes).  Profiles
+ * are processed in chunks of chunk_profiles (0 = automatic) through two device staging slots: the host-to-device
+ * copy of chunk k+1, the kernels of chunk k and the device-to-host copy of chunk k-1 run concurrently on three
+ * streams, with no staging memcpy on the host.  This is the entry the profile-sharded multi-GPU operator uses:
+ * each rank passes its shard and a vh_out that points into one page-locked result buffer shared by all ranks
+ * ("final host gather", no collective on the data path).
+ *   vh_profile_stride   doubles between consecutive profiles' rows in vh_out (0 = n_freq, dense); a larger
+ *                       stride lets interleaved shards land in place in the gathered [P x n_freq] array
+ *   cuda_stream         compute stream (NULL = the ctx's own).  Work is ordered after what is already enqueued
+ *                       there, and the stream is made to wait for the last copy-out, so "after this call in
+ *                       stream order" means "results delivered"
+ *   synchronize         non-zero: return after the results are in vh_out / status
+ */
+int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
+                        const double* den, const double* bmag, const double* bpsi, const double* alt,
+                        int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode, int n_points,
+                        unsigned flags, int64_t chunk_profiles, double* vh_out, int64_t vh_profile_stride, int* status,
+                        void* cuda_stream, int synchronize);
+
+/* Page-lock (cudaHostRegister, portable) / release a host range owned by the caller, e.g. the POSIX shared-memory
+ * segment in which the ranks of one node assemble the [P x n_freq] result of the profile-sharded operator. */
+int prhf_host_register(void* ptr, size_t bytes);
+int prhf_host_unregister(void* ptr);
+
+/*
  * Elementwise phase / group refractive index on DEVICE buffers (replaces find_mu_mup,
  * library.py:161-256, magnetised branch or isotropic branch chosen by the caller through
  * `isotropic`, because the reference decides it from the whole array, library.py:201).

@@ -16,6 +16,8 @@ from pyrayhf_b200 import library  # noqa: E402,F401
 from pyrayhf_b200.library import (  # noqa: E402,F401
     vertical_forward_operator,
     vertical_forward_operator_batched,
+    vertical_forward_operator_streamed,
+    pinned_empty,
     find_mu_mup,
     residual_VH_batched,
     brute_force_fit,

@@ -22,7 +22,8 @@ FLAG_LITERAL = 1
 EXPORTED_SYMBOLS = (
     "prhf_version", "prhf_error_string", "prhf_last_cuda_error", "prhf_ctx_create",
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
-    "prhf_vfo_host_f64", "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
+    "prhf_vfo_host_f64", "prhf_vfo_stream_f64", "prhf_host_register", "prhf_host_unregister",
+    "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
     "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64",
     "prhf_den2freq_f64", "prhf_find_x_f64", "prhf_find_y_f64", "prhf_smooth_grid_f64",
     "prhf_regrid_f64", "prhf_find_vh_f64", "prhf_synth_profiles_f64",
@@ -83,6 +84,12 @@ def load():
         L.prhf_vfo_f64.restype = _i
         L.prhf_vfo_host_f64.argtypes = vfo_args
         L.prhf_vfo_host_f64.restype = _i
+        L.prhf_vfo_stream_f64.argtypes = vfo_args[:14] + [_i64, _vp, _i64, _vp, _vp, _i]
+        L.prhf_vfo_stream_f64.restype = _i
+        L.prhf_host_register.argtypes = [_vp, ctypes.c_size_t]
+        L.prhf_host_register.restype = _i
+        L.prhf_host_unregister.argtypes = [_vp]
+        L.prhf_host_unregister.restype = _i
         L.prhf_mu_mup_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _u, _vp, _vp, _vp]
         L.prhf_mu_mup_f64.restype = _i
         L.prhf_measure_fp64_peak.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
@@ -206,3 +213,15 @@ def context(device=-1):
                 ctx = Context(device)
                 _contexts[key] = ctx
     return ctx
+
+
+def host_register(addr, nbytes):
+    """Page-lock a host range this process owns (cudaHostRegister, portable)."""
+    L = load()
+    rc = L.prhf_host_register(_vp(addr), int(nbytes))
+    if rc != OK:
+        raise PrhfError(rc, "cudaHostRegister failed for %d bytes" % nbytes)
+
+
+def host_unregister(addr):
+    load().prhf_host_unregister(_vp(addr))

@@ -73,6 +73,19 @@ struct prhf_ctx {
   std::map<std::array<int64_t, 9>, GraphEntry> graphs;
   int max_smem_per_sm = 0;
   int planned_max_rows = 4096;       // PRHF_PLANNED_MAX_ROWS
+  // cross-stream guard: the K1 -> K2 hand-off buffers above are shared by every call on this ctx, so a call that
+  // arrives on another stream than the previous one first waits (on the device) for that one to drain
+  cudaEvent_t busy_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool have_last_stream = false;
+  // streaming entry (prhf_vfo_stream_f64): two device staging slots, a copy-in and a copy-out stream, events
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr;
+  char* slot_buf[2] = {nullptr, nullptr};
+  size_t slot_cap = 0;
+  char* shared_buf = nullptr;        // device copies of a shared freq / alt vector given on the host
+  size_t shared_cap = 0;
 };
 
 namespace {
@@ -314,6 +327,17 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   if (ctx->row_span) cudaFree(ctx->row_span);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+    if (ctx->ev_k[k]) cudaEventDestroy(ctx->ev_k[k]);
+    if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+    if (ctx->slot_buf[k]) cudaFree(ctx->slot_buf[k]);
+  }
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->busy_ev) cudaEventDestroy(ctx->busy_ev);
+  if (ctx->shared_buf) cudaFree(ctx->shared_buf);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -366,10 +390,12 @@ int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* c
   return PRHF_OK;
 }
 
-int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride, const double* den,
-                 const double* bmag, const double* bpsi, const double* alt, int64_t alt_profile_stride,
-                 int64_t n_profiles, int n_alt, int mode, int n_points, unsigned flags, double* vh_out, int* status,
-                 void* cuda_stream) {
+// The launch sequence of one call (row setup + tiles, or the single-launch kernel) on `cuda_stream`.  Shared by the
+// device entry, the host entry (under stream capture) and the streaming entry.
+static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride, const double* den,
+                       const double* bmag, const double* bpsi, const double* alt, int64_t alt_profile_stride,
+                       int64_t n_profiles, int n_alt, int mode, int n_points, unsigned flags, double* vh_out, int* status,
+                       void* cuda_stream) {
   int rc = validate(ctx, freq_mhz, n_freq, den, bmag, bpsi, alt, n_profiles, n_alt, mode, n_points, vh_out);
   if (rc != PRHF_OK) return rc;
   if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
@@ -556,6 +582,39 @@ int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq
   return PRHF_OK;
 }
 
+// The hand-off buffers of a ctx (ProfileRecord, row spans, partials, counters, live list) serve one launch sequence
+// at a time.  Calls that arrive on different streams are therefore ordered on the device: the newcomer's stream
+// waits for the event recorded behind the previous call.  Same-stream calls pay one event record (~1 us of host time).
+static int stream_guard_enter(prhf_ctx* ctx, cudaStream_t stream) {
+  if (ctx->have_last_stream && ctx->last_stream != stream && ctx->busy_ev)
+    PRHF_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->busy_ev, 0));
+  return PRHF_OK;
+}
+static int stream_guard_leave(prhf_ctx* ctx, cudaStream_t stream) {
+  if (!ctx->busy_ev) PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->busy_ev, cudaEventDisableTiming));
+  PRHF_CUDA(ctx, cudaEventRecord(ctx->busy_ev, stream));
+  ctx->last_stream = stream;
+  ctx->have_last_stream = true;
+  return PRHF_OK;
+}
+
+int prhf_vfo_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride, const double* den,
+                 const double* bmag, const double* bpsi, const double* alt, int64_t alt_profile_stride,
+                 int64_t n_profiles, int n_alt, int mode, int n_points, unsigned flags, double* vh_out, int* status,
+                 void* cuda_stream) {
+  int rc = validate(ctx, freq_mhz, n_freq, den, bmag, bpsi, alt, n_profiles, n_alt, mode, n_points, vh_out);
+  if (rc != PRHF_OK) return rc;
+  if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  rc = stream_guard_enter(ctx, stream);
+  if (rc != PRHF_OK) return rc;
+  rc = vfo_enqueue(ctx, freq_mhz, n_freq, freq_profile_stride, den, bmag, bpsi, alt, alt_profile_stride, n_profiles, n_alt,
+                   mode, n_points, flags, vh_out, status, cuda_stream);
+  if (rc != PRHF_OK) return rc;
+  return stream_guard_leave(ctx, stream);
+}
+
 int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
                       const double* den, const double* bmag, const double* bpsi, const double* alt,
                       int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode, int n_points,
@@ -564,6 +623,8 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
   if (rc != PRHF_OK) return rc;
   if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
   DeviceGuard g(ctx->device);
+  rc = stream_guard_enter(ctx, ctx->stream);                  // a device-entry call may still be in flight elsewhere
+  if (rc != PRHF_OK) return rc;
 
   // Profiles are processed in chunks through one packed arena:
   //   inputs  [freq | alt | den | bmag | bpsi]   (one H2D copy per chunk)
@@ -621,7 +682,7 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     int* d_st = (int*)(out_base + out_off + d8 * (size_t)n_freq * np);
     auto enqueue = [&]() -> int {
       PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->d_arena, ctx->h_arena, off, cudaMemcpyHostToDevice, ctx->stream));
-      return prhf_vfo_f64(ctx, (const double*)(ctx->d_arena + o_freq), n_freq, freq_shared ? 0 : n_freq,
+      return vfo_enqueue(ctx, (const double*)(ctx->d_arena + o_freq), n_freq, freq_shared ? 0 : n_freq,
                           (const double*)(ctx->d_arena + o_den), (const double*)(ctx->d_arena + o_b),
                           (const double*)(ctx->d_arena + o_psi), (const double*)(ctx->d_arena + o_alt),
                           alt_shared ? 0 : n_alt, np, n_alt, mode, n_points, flags, d_vh, d_st, ctx->stream);
@@ -688,6 +749,203 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     PRHF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(vh_out + p0 * n_freq, ctx->h_arena + out_off, d8 * (size_t)n_freq * np);
     if (status) memcpy(status + p0, ctx->h_arena + out_off + d8 * (size_t)n_freq * np, sizeof(int) * (size_t)np);
+  }
+  ctx->have_last_stream = false;                              // everything on this ctx has drained
+  return PRHF_OK;
+}
+
+// ---- streaming entry -------------------------------------------------------------------------------------------
+namespace {
+bool on_device(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// rows x count doubles, source row stride src_stride, destination row stride dst_stride (both in doubles)
+cudaError_t copy_rows(double* dst, int64_t dst_stride, const double* src, int64_t src_stride, size_t count, int64_t rows,
+                      cudaMemcpyKind kind, cudaStream_t st) {
+  if (rows <= 0 || count == 0) return cudaSuccess;
+  if ((src_stride == (int64_t)count && dst_stride == (int64_t)count) || rows == 1)
+    return cudaMemcpyAsync(dst, src, sizeof(double) * count * (size_t)rows, kind, st);
+  return cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)dst_stride, src, sizeof(double) * (size_t)src_stride,
+                           sizeof(double) * count, (size_t)rows, kind, st);
+}
+}  // namespace
+
+int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t freq_profile_stride,
+                        const double* den, const double* bmag, const double* bpsi, const double* alt,
+                        int64_t alt_profile_stride, int64_t n_profiles, int n_alt, int mode, int n_points,
+                        unsigned flags, int64_t chunk_profiles, double* vh_out, int64_t vh_profile_stride, int* status,
+                        void* cuda_stream, int synchronize) {
+  int rc = validate(ctx, freq_mhz, n_freq, den, bmag, bpsi, alt, n_profiles, n_alt, mode, n_points, vh_out);
+  if (rc != PRHF_OK) return rc;
+  if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
+  if (vh_profile_stride == 0) vh_profile_stride = n_freq;
+  if (vh_profile_stride < n_freq || chunk_profiles < 0) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  cudaStream_t sk = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  const size_t d8 = sizeof(double);
+  const bool freq_shared = (freq_profile_stride == 0), alt_shared = (alt_profile_stride == 0);
+  const bool den_dev = on_device(den), b_dev = on_device(bmag), psi_dev = on_device(bpsi);
+  const bool freq_dev = on_device(freq_mhz), alt_dev = on_device(alt);
+  const bool vh_dev = on_device(vh_out), st_dev = status ? on_device(status) : true;
+  const bool vh_direct = vh_dev && vh_profile_stride == n_freq;   // the kernels write the caller's buffer themselves
+  rc = stream_guard_enter(ctx, sk);
+  if (rc != PRHF_OK) return rc;
+
+  // chunking: enough chunks for the copies to hide behind the kernels, chunks large enough to fill the GPU
+  int64_t chunk = chunk_profiles;
+  const size_t per_prof = d8 * ((den_dev ? 0 : (size_t)n_alt) + (b_dev ? 0 : (size_t)n_alt) + (psi_dev ? 0 : (size_t)n_alt) +
+                                ((alt_shared || alt_dev) ? 0 : (size_t)n_alt) +
+                                ((freq_shared || freq_dev) ? 0 : (size_t)n_freq) + (vh_direct ? 0 : (size_t)n_freq)) +
+                          ((status && st_dev) ? 0 : sizeof(int));
+  if (chunk == 0) {
+    chunk = std::min<int64_t>(4096, std::max<int64_t>(256, (n_profiles + 7) / 8));
+    if (per_prof == 0) chunk = n_profiles;                    // nothing to stage: one launch sequence
+  }
+  if (per_prof > 0) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)(((size_t)512 << 20) / per_prof)));
+  chunk = std::min<int64_t>(chunk, n_profiles);
+  const int64_t n_chunks = (n_profiles + chunk - 1) / chunk;
+
+  // resources: streams, events, two staging slots, device copies of shared host vectors
+  if (!ctx->s_in) {
+    PRHF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    PRHF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+      PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[k], cudaEventDisableTiming));
+      PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming));
+    }
+    PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+  }
+  const size_t slot_bytes = ((per_prof * (size_t)chunk + 255) & ~(size_t)255) + 256;
+  if (slot_bytes > ctx->slot_cap) {
+    PRHF_CUDA(ctx, cudaDeviceSynchronize());
+    for (int k = 0; k < 2; ++k) {
+      if (ctx->slot_buf[k]) cudaFree(ctx->slot_buf[k]);
+      ctx->slot_buf[k] = nullptr;
+    }
+    ctx->slot_cap = 0;
+    for (int k = 0; k < 2; ++k) PRHF_CUDA(ctx, cudaMalloc(&ctx->slot_buf[k], slot_bytes));
+    ctx->slot_cap = slot_bytes;
+  }
+  const size_t shared_bytes = d8 * (((freq_shared && !freq_dev) ? (size_t)n_freq : 0) + ((alt_shared && !alt_dev) ? (size_t)n_alt : 0));
+  if (shared_bytes > ctx->shared_cap) {
+    PRHF_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->shared_buf) cudaFree(ctx->shared_buf);
+    ctx->shared_buf = nullptr;
+    ctx->shared_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->shared_buf, shared_bytes + 256));
+    ctx->shared_cap = shared_bytes;
+  }
+
+  // everything below is ordered after what the caller already enqueued on the compute stream (device inputs may
+  // still be in production there)
+  PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_start, sk));
+  PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+  PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+  const double* d_freq_shared = freq_mhz;
+  const double* d_alt_shared = alt;
+  {
+    char* sb = ctx->shared_buf;
+    if (freq_shared && !freq_dev) {
+      PRHF_CUDA(ctx, cudaMemcpyAsync(sb, freq_mhz, d8 * (size_t)n_freq, cudaMemcpyHostToDevice, ctx->s_in));
+      d_freq_shared = (const double*)sb;
+      sb += d8 * (size_t)n_freq;
+    }
+    if (alt_shared && !alt_dev) {
+      PRHF_CUDA(ctx, cudaMemcpyAsync(sb, alt, d8 * (size_t)n_alt, cudaMemcpyHostToDevice, ctx->s_in));
+      d_alt_shared = (const double*)sb;
+    }
+  }
+
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int slot = (int)(c & 1);
+    const int64_t p0 = c * chunk, np = std::min(chunk, n_profiles - p0);
+    char* base = ctx->slot_buf[slot];
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+      char* q = base + off;
+      off += (bytes + 15) & ~(size_t)15;
+      return q;
+    };
+    // ---- copy-in stream: the slot's inputs are free once the kernels of chunk c-2 have finished ----
+    if (c >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[slot], 0));
+    auto stage = [&](const double* src, bool dev, int64_t stride, size_t count, const double** out) -> cudaError_t {
+      if (dev) {
+        *out = src + p0 * stride;
+        return cudaSuccess;
+      }
+      double* dst = (double*)carve(d8 * count * (size_t)np);
+      *out = dst;
+      return copy_rows(dst, (int64_t)count, src + p0 * stride, stride, count, np, cudaMemcpyHostToDevice, ctx->s_in);
+    };
+    const double *c_den, *c_b, *c_psi, *c_alt = d_alt_shared, *c_freq = d_freq_shared;
+    int64_t c_alt_stride = 0, c_freq_stride = 0;
+    PRHF_CUDA(ctx, stage(den, den_dev, n_alt, (size_t)n_alt, &c_den));
+    PRHF_CUDA(ctx, stage(bmag, b_dev, n_alt, (size_t)n_alt, &c_b));
+    PRHF_CUDA(ctx, stage(bpsi, psi_dev, n_alt, (size_t)n_alt, &c_psi));
+    if (!alt_shared) {
+      PRHF_CUDA(ctx, stage(alt, alt_dev, alt_profile_stride, (size_t)n_alt, &c_alt));
+      c_alt_stride = alt_dev ? alt_profile_stride : n_alt;
+    }
+    if (!freq_shared) {
+      PRHF_CUDA(ctx, stage(freq_mhz, freq_dev, freq_profile_stride, (size_t)n_freq, &c_freq));
+      c_freq_stride = freq_dev ? freq_profile_stride : n_freq;
+    }
+    PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+    double* c_vh = vh_direct ? vh_out + p0 * vh_profile_stride : (double*)carve(d8 * (size_t)n_freq * (size_t)np);
+    int* c_st = status ? (st_dev ? status + p0 : (int*)carve(sizeof(int) * (size_t)np)) : nullptr;
+    // ---- compute stream: inputs of this chunk have landed, outputs of chunk c-2 have left the slot ----
+    PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_in[slot], 0));
+    if (c >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_out[slot], 0));
+    rc = vfo_enqueue(ctx, c_freq, n_freq, c_freq_stride, c_den, c_b, c_psi, c_alt, c_alt_stride, np, n_alt, mode, n_points,
+                     flags, c_vh, c_st, sk);
+    if (rc != PRHF_OK) return rc;
+    PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_k[slot], sk));
+    // ---- copy-out stream ----
+    PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[slot], 0));
+    if (!vh_direct)
+      PRHF_CUDA(ctx, copy_rows(vh_out + p0 * vh_profile_stride, vh_profile_stride, c_vh, n_freq, (size_t)n_freq, np,
+                               vh_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_out));
+    if (status && !st_dev)
+      PRHF_CUDA(ctx, cudaMemcpyAsync(status + p0, c_st, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost, ctx->s_out));
+    PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+  }
+  // the compute stream ends behind the last copies, so "after this call" in stream order means "results delivered"
+  PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_out[(n_chunks - 1) & 1], 0));
+  if (n_chunks >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_out[(n_chunks - 2) & 1], 0));
+  rc = stream_guard_leave(ctx, sk);
+  if (rc != PRHF_OK) return rc;
+  if (synchronize) {
+    PRHF_CUDA(ctx, cudaStreamSynchronize(sk));
+    ctx->have_last_stream = false;
+  }
+  return PRHF_OK;
+}
+
+// Page-lock / release a host range the caller owns (the shared-memory result buffer of the sharded operator).
+int prhf_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return PRHF_ERR_INVALID_ARG;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return PRHF_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return PRHF_ERR_CUDA;
+  }
+  return PRHF_OK;
+}
+int prhf_host_unregister(void* ptr) {
+  if (!ptr) return PRHF_ERR_INVALID_ARG;
+  if (cudaHostUnregister(ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return PRHF_ERR_CUDA;
   }
   return PRHF_OK;
 }

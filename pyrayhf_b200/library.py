@@ -131,38 +131,89 @@ def _is_torch_tensor(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+def _n_points_checked(n_points):
+    n_points = int(n_points)
+    if n_points < 1:
+        # np.nanmax of an empty [F x 0] array at library.py:201 -- same error as the single-profile entry
+        raise ValueError("zero-size array to reduction operation fmax which has no identity")
+    return n_points
+
+
+def _check_batched_shapes(freq, den, bmag, bpsi, alt):
+    """Shapes the batched entries accept: den [P, A]; bmag / bpsi [P, A] or [A]; freq [F], (1, F) or [P, F];
+    alt [A] or [P, A].  Returns (n_prof, n_alt, n_freq).  Raw pointers go to the C ABI after this, so every
+    mismatch must be caught here (a short buffer would be read out of bounds)."""
+    if den.ndim != 2:
+        raise ValueError("den must be [n_profiles, n_alt], got shape %s" % (tuple(den.shape),))
+    n_prof, n_alt = int(den.shape[0]), int(den.shape[1])
+    for name, v in (("bmag", bmag), ("bpsi", bpsi)):
+        if tuple(v.shape) not in ((n_prof, n_alt), (n_alt,)):
+            raise ValueError("%s must be [n_profiles, n_alt] = %s or [n_alt], got %s"
+                             % (name, (n_prof, n_alt), tuple(v.shape)))
+    if tuple(alt.shape) not in ((n_prof, n_alt), (n_alt,)):
+        raise ValueError("alt must be [n_alt] = (%d,) or [n_profiles, n_alt], got %s" % (n_alt, tuple(alt.shape)))
+    if freq.ndim == 1:
+        n_freq = int(freq.shape[0])
+    elif freq.ndim == 2 and int(freq.shape[0]) in (1, n_prof):
+        n_freq = int(freq.shape[1])
+    else:
+        raise ValueError("freq must be [n_freq], (1, n_freq) or [n_profiles, n_freq], got %s" % (tuple(freq.shape),))
+    return n_prof, n_alt, n_freq
+
+
+def _check_out(out, n_prof, n_freq, want_torch, device=None):
+    import_ok = _is_torch_tensor(out) if want_torch else isinstance(out, np.ndarray)
+    if not import_ok:
+        raise ValueError("out must be a %s" % ("torch tensor on the inputs' device" if want_torch else "numpy array"))
+    if tuple(out.shape) != (n_prof, n_freq):
+        raise ValueError("out must have shape %s, got %s" % ((n_prof, n_freq), tuple(out.shape)))
+    if want_torch:
+        import torch
+        if out.dtype != torch.float64 or not out.is_contiguous() or out.device != device:
+            raise ValueError("out must be a contiguous float64 tensor on %s" % (device,))
+    elif out.dtype != _F64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array")
+
+
 def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
                                       literal=False, errors='raise', return_status=False,
                                       out=None, device=None):
-    """Batched operator: ``den``/``bmag``/``bpsi`` are ``[P, A]``; ``freq`` is ``[F]`` or
-    ``[P, F]``; ``alt`` is ``[A]`` or ``[P, A]``.  Row ``p`` of the ``[P, F]`` result equals
-    the reference called on profile ``p`` alone (peak truncation, unmagnetised switch and
-    error status are per profile).
+    """Batched operator: ``den`` is ``[P, A]``; ``bmag`` / ``bpsi`` are ``[P, A]`` or ``[A]`` (shared by all
+    profiles); ``freq`` is ``[F]`` or ``[P, F]``; ``alt`` is ``[A]`` or ``[P, A]``.  Row ``p`` of the ``[P, F]``
+    result equals the reference called on profile ``p`` alone (peak truncation, unmagnetised switch and
+    error status are per profile).  Anything else raises ``ValueError`` before the C ABI sees a pointer.
 
     Inputs may be numpy arrays (copied through pinned memory, numpy result) or float64
     CUDA torch tensors (used in place on the current stream, torch result, asynchronous).
     ``errors='raise'`` re-raises the reference's per-profile exceptions (needs a host
     sync for torch inputs); ``errors='nan'`` leaves failed profiles as NaN rows.
+
+    A ctx serves one launch sequence at a time: calls issued from one host thread on different torch streams
+    are ordered on the device (the later call's stream waits for the earlier one), they do not overlap.
     """
     code = _mode_code(mode)
-    n_points = int(n_points)
+    n_points = _n_points_checked(n_points)
     flags = _cabi.FLAG_LITERAL if literal else 0
     if _is_torch_tensor(den):
         import torch
         ts = [freq, den, bmag, bpsi, alt]
         for t in ts:
-            if not (_is_torch_tensor(t) and t.is_cuda and t.dtype == torch.float64):
-                raise TypeError("torch inputs must all be float64 CUDA tensors")
-        freq, den, bmag, bpsi, alt = (t.contiguous() for t in ts)
-        n_prof, n_alt = den.shape
-        n_freq = freq.shape[-1]
+            if not (_is_torch_tensor(t) and t.is_cuda and t.dtype == torch.float64 and t.device == den.device):
+                raise TypeError("torch inputs must all be float64 CUDA tensors on one device")
+        n_prof, n_alt, n_freq = _check_batched_shapes(*ts)
+        if bmag.dim() == 1:
+            bmag = bmag.expand(n_prof, n_alt)
+        if bpsi.dim() == 1:
+            bpsi = bpsi.expand(n_prof, n_alt)
+        if freq.dim() == 2 and freq.shape[0] == 1:
+            freq = freq.reshape(-1)
+        freq, den, bmag, bpsi, alt = (t.contiguous() for t in (freq, den, bmag, bpsi, alt))
         dev = den.device
+        if out is not None:
+            _check_out(out, n_prof, n_freq, True, dev)
         vh = out if out is not None else torch.empty((n_prof, n_freq), dtype=torch.float64, device=dev)
         st = torch.zeros(n_prof, dtype=torch.int32, device=dev)
         if n_prof == 0 or n_freq == 0:
-            return (vh, st) if return_status else vh
-        if n_points < 1:
-            vh.fill_(float('nan'))
             return (vh, st) if return_status else vh
         ctx = _cabi.context(dev.index if dev.index is not None else torch.cuda.current_device())
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -177,26 +228,119 @@ def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_po
                 _raise_profile_status(bad)
         return (vh, st) if return_status else vh
 
-    freq, den, bmag, bpsi, alt = (_f64(v) for v in (freq, den, bmag, bpsi, alt))
-    if den.ndim != 2:
-        raise ValueError("den must be [n_profiles, n_alt]")
-    n_prof, n_alt = den.shape
-    n_freq = freq.shape[-1]
-    vh = np.empty((n_prof, n_freq), dtype=np.float64)
+    freq, den, bmag, bpsi, alt = (np.asarray(v, dtype=np.float64) for v in (freq, den, bmag, bpsi, alt))
+    n_prof, n_alt, n_freq = _check_batched_shapes(freq, den, bmag, bpsi, alt)
+    if bmag.ndim == 1:
+        bmag = np.broadcast_to(bmag, den.shape)
+    if bpsi.ndim == 1:
+        bpsi = np.broadcast_to(bpsi, den.shape)
+    if freq.ndim == 2 and freq.shape[0] == 1:
+        freq = freq.reshape(-1)
+    freq, den, bmag, bpsi, alt = (np.ascontiguousarray(v) for v in (freq, den, bmag, bpsi, alt))
+    if out is not None:
+        _check_out(out, n_prof, n_freq, False)
+    vh = out if out is not None else np.empty((n_prof, n_freq), dtype=np.float64)
     st = np.zeros(n_prof, dtype=np.int32)
     if n_prof and n_freq:
-        if n_points < 1:
-            vh.fill(np.nan)
-        else:
-            ctx = _cabi.context(-1 if device is None else device)
-            rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(freq), n_freq, n_freq if freq.ndim == 2 else 0,
-                                           _ptr(den), _ptr(bmag), _ptr(bpsi), _ptr(alt),
-                                           n_alt if alt.ndim == 2 else 0, n_prof, n_alt, code, n_points,
-                                           flags, _ptr(vh), _ptr(st))
-            ctx.check(rc)
+        ctx = _cabi.context(-1 if device is None else device)
+        rc = ctx.lib.prhf_vfo_host_f64(ctx.handle, _ptr(freq), n_freq, n_freq if freq.ndim == 2 else 0,
+                                       _ptr(den), _ptr(bmag), _ptr(bpsi), _ptr(alt),
+                                       n_alt if alt.ndim == 2 else 0, n_prof, n_alt, code, n_points,
+                                       flags, _ptr(vh), _ptr(st))
+        ctx.check(rc)
     if errors == 'raise' and st.any():
         _raise_profile_status(int(st.max()))
     return (vh, st) if return_status else vh
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A page-locked numpy array (backed by a pinned torch tensor): the input / output memory the streaming
+    entry copies from and to at full PCIe rate without a staging pass on the host.  (Without a CUDA device --
+    host-side tests of the sharding logic -- a plain array is returned.)"""
+    import torch
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    if not torch.cuda.is_available():
+        return np.empty(shape, dtype=dtype)
+    tdtype = torch.from_numpy(np.empty(0, dtype=dtype)).dtype
+    return torch.empty(shape, dtype=tdtype, pin_memory=True).numpy()   # .base keeps the pinned allocation alive
+
+
+def _addr_of(x):
+    return _vp(x.data_ptr()) if _is_torch_tensor(x) else _vp(x.ctypes.data)
+
+
+def vertical_forward_operator_streamed(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
+                                       literal=False, errors='raise', return_status=False, out=None,
+                                       out_profile_stride=None, status_out=None, chunk_profiles=0, device=None,
+                                       stream=None, synchronize=True):
+    """The batched operator for LARGE batches whose arrays live on the host (ideally page-locked, see
+    ``pinned_empty``), on the GPU, or a mix: profiles are processed in chunks and the host-to-device copy of the
+    next chunk, the kernels of the current one and the device-to-host copy of the previous one overlap
+    (``prhf_vfo_stream_f64``).  Shapes as ``vertical_forward_operator_batched`` (no ``[A]`` broadcast of
+    ``bmag`` / ``bpsi`` here: pass ``[P, A]``).  float64, C-contiguous numpy arrays or torch tensors (CPU or CUDA).
+
+    ``out`` may be given (numpy / torch, host or device); ``out_profile_stride`` (in doubles) lets the rows land
+    strided in a larger buffer -- the sharded operator passes a slice of the gathered result.  Returns ``out``
+    (a new pinned numpy array when not given).  With ``synchronize=False`` the call returns once everything is
+    enqueued on ``stream`` (a raw CUDA stream handle, default: the ctx's own) and ``errors`` must be ``'nan'``.
+    """
+    code = _mode_code(mode)
+    n_points = _n_points_checked(n_points)
+    flags = _cabi.FLAG_LITERAL if literal else 0
+    arrs = [freq, den, bmag, bpsi, alt]
+    for k, v in enumerate(arrs):
+        if _is_torch_tensor(v):
+            import torch
+            if v.dtype != torch.float64 or not v.is_contiguous():
+                raise TypeError("tensors must be contiguous float64")
+        else:
+            arrs[k] = np.ascontiguousarray(v, dtype=np.float64)
+    freq, den, bmag, bpsi, alt = arrs
+    n_prof, n_alt, n_freq = _check_batched_shapes(freq, den, bmag, bpsi, alt)
+    if tuple(bmag.shape) != (n_prof, n_alt) or tuple(bpsi.shape) != (n_prof, n_alt):
+        raise ValueError("the streaming entry takes bmag / bpsi as [n_profiles, n_alt]")
+    if freq.ndim == 2 and freq.shape[0] == 1 and n_prof != 1:
+        freq = freq.reshape(-1)
+    if device is None:
+        for v in arrs + [out]:
+            if _is_torch_tensor(v) and v.is_cuda:
+                device = v.device.index
+                break
+    stride = n_freq if out_profile_stride is None else int(out_profile_stride)
+    if out is None:
+        if stride != n_freq:
+            raise ValueError("out_profile_stride needs an explicit out buffer")
+        out = pinned_empty((n_prof, n_freq))
+    elif stride == n_freq:
+        if tuple(out.shape) != (n_prof, n_freq):
+            raise ValueError("out must have shape %s, got %s" % ((n_prof, n_freq), tuple(out.shape)))
+    if _is_torch_tensor(out):
+        import torch
+        if out.dtype != torch.float64 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float64 tensor")
+        out_elems = out.numel()
+    else:
+        if out.dtype != _F64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array")
+        out_elems = out.size
+    if n_prof and out_elems < (n_prof - 1) * stride + n_freq:
+        raise ValueError("out is too small for %d profiles at a stride of %d doubles" % (n_prof, stride))
+    st = status_out if status_out is not None else np.zeros(n_prof, dtype=np.int32)
+    if not synchronize and errors == 'raise':
+        raise ValueError("errors='raise' needs synchronize=True")
+    if n_prof and n_freq:
+        ctx = _cabi.context(-1 if device is None else device)
+        rc = ctx.lib.prhf_vfo_stream_f64(ctx.handle, _addr_of(freq), n_freq, n_freq if freq.ndim == 2 else 0,
+                                         _addr_of(den), _addr_of(bmag), _addr_of(bpsi), _addr_of(alt),
+                                         n_alt if alt.ndim == 2 else 0, n_prof, n_alt, code, n_points, flags,
+                                         int(chunk_profiles), _addr_of(out), stride, _addr_of(st),
+                                         _vp(stream) if stream else None, 1 if synchronize else 0)
+        ctx.check(rc)
+    if errors == 'raise':
+        bad = int(st.max()) if n_prof else 0
+        if bad:
+            _raise_profile_status(bad)
+    return (out, st) if return_status else out
 
 
 def find_mu_mup(X, Y, bpsi, mode, y_tol=1e-12, *, literal=False):
