@@ -1,10 +1,13 @@
-"""TEST/BENCH INFRASTRUCTURE ONLY -- timing harness for the CPU baseline legs of bench.py.
+"""TEST/BENCH INFRASTRUCTURE ONLY -- timing harness for the CPU legs of bench.py.
 
-Runs the numpy restatement of the reference (oracle/vfo_oracle.py, same whole-array numpy
-evaluation as PyRayHF/library.py:459-509, bit-identical results) in one process per host core,
-because the reference is single-threaded numpy and "all the host threads it can use" means one
-independent call per core.  Workers are spawned (never forked from a CUDA process) and import
-numpy + the oracle only.
+What is timed is the reference's own ``PyRayHF.library.vertical_forward_operator`` (library.py:459-509), loaded
+from the unmodified copy in ``oracle/_ref`` (``oracle/make_ref.py``; ``kind = "reference"``).  Only when that copy
+is absent does it fall back to the numpy restatement ``oracle/vfo_oracle.py`` (``kind = "port"``: the same
+whole-array numpy evaluation, bit-identical results in the dev container, ~25 % faster because it evaluates sin/cos
+once).  Two figures, as BASELINE.md asks: (a) ONE process, how the reference actually runs; (b) one process per
+host core, one profile per task, the best the reference can do without code changes ("all the host threads it can
+use": the reference is single-threaded numpy).  Workers are spawned (never forked from a CUDA process) and import
+numpy + the reference/oracle only -- nothing of the product package.
 """
 import multiprocessing as mp
 import os
@@ -13,32 +16,70 @@ import warnings
 
 import numpy as np
 
+_FN = None
+
+
+def _operator():
+    """(callable, kind) -- resolved once per process."""
+    global _FN
+    if _FN is None:
+        from oracle import make_ref
+        ref = make_ref.load()
+        if ref is not None:
+            _FN = (ref.vertical_forward_operator, "reference")
+        else:
+            from oracle import vfo_oracle
+            _FN = (vfo_oracle.vertical_forward_operator, "port")
+    return _FN
+
+
+def baseline_kind():
+    from oracle import make_ref
+    return "reference" if os.path.isfile(os.path.join(make_ref.REF_DIR, "PyRayHF", "library.py")) else "port"
+
 
 def _work(args):
-    freq, den, bmag, bpsi, alt, mode, n_points, reps = args
+    freq, den, bmag, bpsi, alt, mode, n_points = args
     warnings.simplefilter("ignore")
-    from oracle import vfo_oracle
+    import logging
+    logging.getLogger("PyRayHF_logger").setLevel(logging.CRITICAL)
+    fn, _ = _operator()
     t0 = time.perf_counter()
-    vh = None
-    for _ in range(reps):
-        vh = vfo_oracle.vertical_forward_operator(freq, den, bmag, bpsi, alt, mode, n_points)
+    vh = fn(freq, den, bmag, bpsi, alt, mode, n_points)
     return time.perf_counter() - t0, vh
 
 
-class NumpyPortPool:
-    """A pool of ``cores`` processes, each evaluating the same rows per pass."""
+def _warm(_):
+    _operator()
+    return os.getpid()
+
+
+def one_process(freq, den, bmag, bpsi, alt, mode, n_points, repeats=3):
+    """Best-of-``repeats`` wall time of one call in THIS process after one warm-up call -> (seconds, vh)."""
+    best, vh = np.inf, None
+    for k in range(repeats + 1):
+        t, vh = _work((freq, den, bmag, bpsi, alt, mode, n_points))
+        if k:
+            best = min(best, t)
+    return best, vh
+
+
+class ReferencePool:
+    """``cores`` spawned processes; ``one_pass`` hands each ONE profile (all its frequencies) and waits for all."""
 
     def __init__(self, cores=None):
         self.cores = cores or os.cpu_count() or 1
         self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_warm, range(self.cores), chunksize=1)          # imports done before anything is timed
+        self.kind = baseline_kind()
 
-    def one_pass(self, freq, den, bmag, bpsi, alt, mode, n_points, reps=1):
-        """Every worker evaluates ``freq`` rows ``reps`` times.  Returns (wall_s, rows_done, vh)."""
-        job = (freq, den, bmag, bpsi, alt, mode, n_points, reps)
+    def one_pass(self, freq, den, bmag, bpsi, alt, mode, n_points):
+        """``den`` / ``bmag`` / ``bpsi`` are ``[k, A]`` with k <= cores profiles.  Returns (wall_s, vh [k, F])."""
+        jobs = [(freq, den[q], bmag[q], bpsi[q], alt, mode, n_points) for q in range(den.shape[0])]
         t0 = time.perf_counter()
-        res = self.pool.map(_work, [job] * self.cores, chunksize=1)
+        res = self.pool.map(_work, jobs, chunksize=1)
         wall = time.perf_counter() - t0
-        return wall, self.cores * reps * freq.size, res[0][1]
+        return wall, np.stack([r[1] for r in res])
 
     def close(self):
         self.pool.close()
