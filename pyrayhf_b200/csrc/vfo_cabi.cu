@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/pyrayhf_b200.h"
 #include "vfo_kernels.h"
@@ -821,7 +822,7 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
     }
     PRHF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
   }
-  const size_t slot_bytes = ((per_prof * (size_t)chunk + 255) & ~(size_t)255) + 256;
+  const size_t slot_bytes = ((per_prof * (size_t)chunk + 255) & ~(size_t)255) + 8 * 256;   // carve() rounds to 256 B
   if (slot_bytes > ctx->slot_cap) {
     PRHF_CUDA(ctx, cudaDeviceSynchronize());
     for (int k = 0; k < 2; ++k) {
@@ -862,18 +863,41 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
     }
   }
 
-  for (int64_t c = 0; c < n_chunks; ++c) {
+  // Developer timeline (PRHF_STREAM_TRACE=1): timing events around the three phases of every chunk, printed to
+  // stderr after the call (forces synchronisation).
+  const bool trace = getenv("PRHF_STREAM_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  mark(sk);                                                   // t = 0
+
+  struct Staged {
+    const double *den, *b, *psi, *alt, *freq;
+    int64_t alt_stride, freq_stride;
+    double* vh;
+    int* st;
+  } staged[2];
+
+  // Issue order is breadth-first: the copy-in of chunk c+1 is enqueued BEFORE the kernels of chunk c, so the copy can
+  // never sit behind them in a hardware queue two streams happen to share.
+  auto issue_copy_in = [&](int64_t c) -> int {
     const int slot = (int)(c & 1);
     const int64_t p0 = c * chunk, np = std::min(chunk, n_profiles - p0);
     char* base = ctx->slot_buf[slot];
     size_t off = 0;
     auto carve = [&](size_t bytes) {
       char* q = base + off;
-      off += (bytes + 15) & ~(size_t)15;
+      off += (bytes + 255) & ~(size_t)255;
       return q;
     };
-    // ---- copy-in stream: the slot's inputs are free once the kernels of chunk c-2 have finished ----
+    // the slot's inputs are free once the kernels of chunk c-2 have finished
     if (c >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[slot], 0));
+    mark(ctx->s_in);
     auto stage = [&](const double* src, bool dev, int64_t stride, size_t count, const double** out) -> cudaError_t {
       if (dev) {
         *out = src + p0 * stride;
@@ -883,36 +907,56 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
       *out = dst;
       return copy_rows(dst, (int64_t)count, src + p0 * stride, stride, count, np, cudaMemcpyHostToDevice, ctx->s_in);
     };
-    const double *c_den, *c_b, *c_psi, *c_alt = d_alt_shared, *c_freq = d_freq_shared;
-    int64_t c_alt_stride = 0, c_freq_stride = 0;
-    PRHF_CUDA(ctx, stage(den, den_dev, n_alt, (size_t)n_alt, &c_den));
-    PRHF_CUDA(ctx, stage(bmag, b_dev, n_alt, (size_t)n_alt, &c_b));
-    PRHF_CUDA(ctx, stage(bpsi, psi_dev, n_alt, (size_t)n_alt, &c_psi));
+    Staged& S = staged[slot];
+    S.alt = d_alt_shared;
+    S.freq = d_freq_shared;
+    S.alt_stride = S.freq_stride = 0;
+    PRHF_CUDA(ctx, stage(den, den_dev, n_alt, (size_t)n_alt, &S.den));
+    PRHF_CUDA(ctx, stage(bmag, b_dev, n_alt, (size_t)n_alt, &S.b));
+    PRHF_CUDA(ctx, stage(bpsi, psi_dev, n_alt, (size_t)n_alt, &S.psi));
     if (!alt_shared) {
-      PRHF_CUDA(ctx, stage(alt, alt_dev, alt_profile_stride, (size_t)n_alt, &c_alt));
-      c_alt_stride = alt_dev ? alt_profile_stride : n_alt;
+      PRHF_CUDA(ctx, stage(alt, alt_dev, alt_profile_stride, (size_t)n_alt, &S.alt));
+      S.alt_stride = alt_dev ? alt_profile_stride : n_alt;
     }
     if (!freq_shared) {
-      PRHF_CUDA(ctx, stage(freq_mhz, freq_dev, freq_profile_stride, (size_t)n_freq, &c_freq));
-      c_freq_stride = freq_dev ? freq_profile_stride : n_freq;
+      PRHF_CUDA(ctx, stage(freq_mhz, freq_dev, freq_profile_stride, (size_t)n_freq, &S.freq));
+      S.freq_stride = freq_dev ? freq_profile_stride : n_freq;
     }
+    mark(ctx->s_in);
     PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
-    double* c_vh = vh_direct ? vh_out + p0 * vh_profile_stride : (double*)carve(d8 * (size_t)n_freq * (size_t)np);
-    int* c_st = status ? (st_dev ? status + p0 : (int*)carve(sizeof(int) * (size_t)np)) : nullptr;
+    S.vh = vh_direct ? vh_out + p0 * vh_profile_stride : (double*)carve(d8 * (size_t)n_freq * (size_t)np);
+    S.st = status ? (st_dev ? status + p0 : (int*)carve(sizeof(int) * (size_t)np)) : nullptr;
+    return PRHF_OK;
+  };
+
+  rc = issue_copy_in(0);
+  if (rc != PRHF_OK) return rc;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int slot = (int)(c & 1);
+    const int64_t p0 = c * chunk, np = std::min(chunk, n_profiles - p0);
+    if (c + 1 < n_chunks) {
+      rc = issue_copy_in(c + 1);
+      if (rc != PRHF_OK) return rc;
+    }
+    const Staged& S = staged[slot];
     // ---- compute stream: inputs of this chunk have landed, outputs of chunk c-2 have left the slot ----
     PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_in[slot], 0));
     if (c >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_out[slot], 0));
-    rc = vfo_enqueue(ctx, c_freq, n_freq, c_freq_stride, c_den, c_b, c_psi, c_alt, c_alt_stride, np, n_alt, mode, n_points,
-                     flags, c_vh, c_st, sk);
+    mark(sk);
+    rc = vfo_enqueue(ctx, S.freq, n_freq, S.freq_stride, S.den, S.b, S.psi, S.alt, S.alt_stride, np, n_alt, mode, n_points,
+                     flags, S.vh, S.st, sk);
     if (rc != PRHF_OK) return rc;
+    mark(sk);
     PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_k[slot], sk));
     // ---- copy-out stream ----
     PRHF_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[slot], 0));
+    mark(ctx->s_out);
     if (!vh_direct)
-      PRHF_CUDA(ctx, copy_rows(vh_out + p0 * vh_profile_stride, vh_profile_stride, c_vh, n_freq, (size_t)n_freq, np,
+      PRHF_CUDA(ctx, copy_rows(vh_out + p0 * vh_profile_stride, vh_profile_stride, S.vh, n_freq, (size_t)n_freq, np,
                                vh_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_out));
     if (status && !st_dev)
-      PRHF_CUDA(ctx, cudaMemcpyAsync(status + p0, c_st, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost, ctx->s_out));
+      PRHF_CUDA(ctx, cudaMemcpyAsync(status + p0, S.st, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost, ctx->s_out));
+    mark(ctx->s_out);
     PRHF_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
   }
   // the compute stream ends behind the last copies, so "after this call" in stream order means "results delivered"
@@ -920,9 +964,28 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
   if (n_chunks >= 2) PRHF_CUDA(ctx, cudaStreamWaitEvent(sk, ctx->ev_out[(n_chunks - 2) & 1], 0));
   rc = stream_guard_leave(ctx, sk);
   if (rc != PRHF_OK) return rc;
-  if (synchronize) {
+  if (synchronize || trace) {
     PRHF_CUDA(ctx, cudaStreamSynchronize(sk));
     ctx->have_last_stream = false;
+  }
+  if (trace) {
+    // event order: [0] start, then per copy-in 2 marks, per chunk 2 compute + 2 copy-out marks, in issue order
+    fprintf(stderr, "prhf stream trace: %lld chunks of %lld profiles (ms since the call started)\n", (long long)n_chunks,
+            (long long)chunk);
+    std::vector<float> t(tev.size(), 0.f);
+    for (size_t k = 1; k < tev.size(); ++k) cudaEventElapsedTime(&t[k], tev[0], tev[k]);
+    // issue order: in(0): 1,2 ; then for c: [in(c+1): 2 marks if any], k(c): 2, out(c): 2
+    size_t k = 1;
+    std::vector<float> in_b(n_chunks), in_e(n_chunks), k_b(n_chunks), k_e(n_chunks), o_b(n_chunks), o_e(n_chunks);
+    in_b[0] = t[k++]; in_e[0] = t[k++];
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      if (c + 1 < n_chunks) { in_b[c + 1] = t[k++]; in_e[c + 1] = t[k++]; }
+      k_b[c] = t[k++]; k_e[c] = t[k++]; o_b[c] = t[k++]; o_e[c] = t[k++];
+    }
+    for (int64_t c = 0; c < n_chunks; ++c)
+      fprintf(stderr, "  chunk %2lld  copy-in %8.3f -> %8.3f   kernels %8.3f -> %8.3f   copy-out %8.3f -> %8.3f\n",
+              (long long)c, in_b[c], in_e[c], k_b[c], k_e[c], o_b[c], o_e[c]);
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
   }
   return PRHF_OK;
 }

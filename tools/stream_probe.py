@@ -54,6 +54,11 @@ def main():
 
     dev_args = (t_freq, den, bmag, bpsi, t_alt)
     host_args = (freq, h[0], h[1], h[2], alt)
+    if len(sys.argv) > 2 and sys.argv[2] == "quick":
+        for n_points in (20000, 200):
+            run("device inputs -> pinned out", dev_args, n_points, 2048, reps=1)
+            run("pinned inputs -> pinned out", host_args, n_points, 2048, reps=1)
+        return
     for n_points in (20000, 200):
         for chunk in (0, 1024, 2048, 4096, 8192):
             run("device inputs -> pinned out", dev_args, n_points, chunk)
