@@ -472,6 +472,41 @@ def config3_block(torch, dev, stream, synth, flush):
     return block
 
 
+def inversion_block(torch, dev, synth):
+    """one brute-force fit as minimize_parameters runs it (library.py:672-825) -- a 31 x 31 grid of
+    (hmF2, B_bot) candidates x the observed frequencies, O-mode, n_points = 200 (the reference's default) -- as one
+    device pipeline: profiles built on the GPU, forward operator, residual, argmin; 16 bytes come back per fit."""
+    import pyrayhf_b200 as prhf
+    alt, freq = synth.default_alt(), synth.default_freq()
+    _, bmag, bpsi = synth.profiles_at([20.0], [0.0], alt)
+    bmag, bpsi = bmag[0], bpsi[0]
+    builder = prhf.chapman_profile_builder(3.0)
+    nm_true = (9.6e6 / 8.97866275) ** 2
+    truth = builder(nm_true, np.array([301.3]), np.array([47.4]), alt).cpu().numpy()[0]
+    out = {"workload": "31 x 31 (hmF2, B_bot) brute grid = 961 candidate profiles per fit, O-mode, Chapman profile "
+                       "builder on the device, observations = the frequencies of 0.1-17.4 MHz that reflect"}
+    for n_points in (200, 2000):
+        vh_true = prhf.vertical_forward_operator(freq, truth, bmag, bpsi, alt, 'O', n_points)
+        f_in, obs = prhf.inversion.sort_observations(freq, vh_true)
+        nm = prhf.nmf2_from_max_frequency(f_in[-1], alt, bmag, 310.0, 'O')
+        hm_grid, bb_grid = np.linspace(279.0, 341.0, 31), np.linspace(40.0, 55.0, 31)
+        fit = lambda: prhf.brute_force_search(f_in, obs, alt, bmag, bpsi, nm, hm_grid, bb_grid, builder, 'O', n_points)  # noqa: E731
+        for _ in range(3):
+            res = fit()
+        torch.cuda.synchronize()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = fit()
+        dt = (time.perf_counter() - t0) / reps
+        out["n%d" % n_points] = {"ms_per_fit": 1e3 * dt, "fits_per_s": 1.0 / dt, "candidates_per_s": 961 / dt,
+                                 "vh_per_s": 961 * f_in.size / dt, "frequencies": int(f_in.size),
+                                 "d2h_bytes_per_fit": 16,
+                                 "h2d_bytes_per_fit": int(961 * 5 * 8 + (4 * alt.size + 2 * f_in.size) * 8),
+                                 "best": [res[0], res[1]]}
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -703,8 +738,7 @@ def run_b200_arm(args):
             sf, sd, sb, sp_, sa, _ = single
             line["next_rows"] = next_rows_section(torch, dev, stream, ctx, sf, sd, sb, sp_, sa,
                                                   with_cpu=not args.no_cpu_baseline)
-            if hasattr(pyrayhf_b200, "bench_inversion"):
-                line["inversion"] = pyrayhf_b200.bench_inversion(torch, dev, stream)
+            line["inversion"] = inversion_block(torch, dev, synth)
     line["clocks"] = clocks.summary()
     emit(line)
     op.close()

@@ -221,6 +221,14 @@ int prhf_snell_f64(prhf_ctx* ctx, const double* f0_hz, const double* elevation_d
 int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_obs, int64_t n_profiles, int n_freq,
                       double* residual_out, double* chi2_out, void* cuda_stream);
 
+/*
+ * Grid node with the smallest objective on DEVICE buffers: the selection step of lmfit's brute-force search as
+ * minimize_parameters uses it (library.py:794-798; scipy.optimize.brute takes the argmin of the raveled grid, first
+ * minimum wins).  values [n] (e.g. chi2_out of prhf_residual_f64); NaN entries are skipped.
+ * out2 [2] (device): {index as a double, -1 when every entry is NaN; the minimum, NaN when none}.
+ */
+int prhf_argmin_f64(prhf_ctx* ctx, const double* values, int64_t n, double* out2, void* cuda_stream);
+
 /* Device FP64 FMA throughput probe used for the roofline denominator: runs a dependent-free DFMA
  * kernel and returns the measured TFLOP/s (2 flop per FMA). */
 int prhf_measure_fp64_peak(prhf_ctx* ctx, double* tflops_out);

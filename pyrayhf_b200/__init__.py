@@ -20,9 +20,18 @@ from pyrayhf_b200.library import (  # noqa: E402,F401
     pinned_empty,
     find_mu_mup,
     residual_VH_batched,
-    brute_force_fit,
     install,
     uninstall,
+)
+from pyrayhf_b200 import inversion  # noqa: E402,F401
+from pyrayhf_b200.inversion import (  # noqa: E402,F401
+    brute_force_fit,
+    brute_force_search,
+    brute_grid,
+    chapman_profile_builder,
+    freq2den,
+    minimize_parameters,
+    nmf2_from_max_frequency,
 )
 from pyrayhf_b200 import stages  # noqa: E402,F401
 from pyrayhf_b200.stages import (  # noqa: E402,F401

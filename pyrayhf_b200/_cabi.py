@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "prhf_ctx_destroy", "prhf_max_n_alt", "prhf_grid_multiplier_f64", "prhf_vfo_f64",
     "prhf_vfo_host_f64", "prhf_vfo_stream_f64", "prhf_host_register", "prhf_host_unregister",
     "prhf_mu_mup_f64", "prhf_measure_fp64_peak", "prhf_launch_count",
-    "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64",
+    "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64", "prhf_argmin_f64",
     "prhf_den2freq_f64", "prhf_find_x_f64", "prhf_find_y_f64", "prhf_smooth_grid_f64",
     "prhf_regrid_f64", "prhf_find_vh_f64", "prhf_synth_profiles_f64",
     "prhf_snell_f64",
@@ -101,6 +101,8 @@ def load():
         L.prhf_kernel_timing.restype = _i
         L.prhf_residual_f64.argtypes = [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]
         L.prhf_residual_f64.restype = _i
+        L.prhf_argmin_f64.argtypes = [_vp, _vp, _i64, _vp, _vp]
+        L.prhf_argmin_f64.restype = _i
         _d = ctypes.c_double
         L.prhf_den2freq_f64.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp]
         L.prhf_den2freq_f64.restype = _i

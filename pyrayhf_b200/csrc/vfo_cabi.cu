@@ -1219,6 +1219,14 @@ int prhf_residual_f64(prhf_ctx* ctx, const double* vh_model, const double* vh_ob
   return PRHF_OK;
 }
 
+int prhf_argmin_f64(prhf_ctx* ctx, const double* values, int64_t n, double* out2, void* cuda_stream) {
+  if (!ctx || n < 0 || !out2 || (n > 0 && !values)) return PRHF_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  PRHF_CUDA(ctx, prhf::launch_argmin(values, n, out2, (cudaStream_t)cuda_stream));
+  ctx->launches++;
+  return PRHF_OK;
+}
+
 int prhf_selftest_math(prhf_ctx* ctx, double* max_rel_err6) {
   if (!ctx || !max_rel_err6) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);

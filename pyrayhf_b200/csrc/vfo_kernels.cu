@@ -1556,6 +1556,40 @@ __global__ void residual_kernel(const double* __restrict__ vh, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// argmin of the brute-force objective (lmfit's brute search at lib:794-798 takes the grid node with the smallest
+// sum of squared residuals; scipy.optimize.brute: argmin of the raveled grid, first minimum wins).  NaN scores
+// (a candidate whose every model height is NaN, or a failed profile) are skipped; out = {index or -1, value}.
+// One CTA: the candidate grids of this path have 10^2 .. 10^5 nodes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) argmin_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+  double best = CUDART_INF;
+  long long bi = -1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = v[i];
+    if (x == x && (bi < 0 || x < best)) { best = x; bi = i; }     // ascending i per thread: first minimum kept
+  }
+  __shared__ double s_v[32];
+  __shared__ long long s_i[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      const double ov = s_v[k];
+      const long long oi = s_i[k];
+      if (oi >= 0 && (bi < 0 || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+    }
+    out[0] = (double)bi;
+    out[1] = (bi >= 0) ? best : CUDART_NAN;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 FMA throughput probe (roofline denominator)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double seed) {
@@ -1748,6 +1782,11 @@ cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_pr
   int64_t blocks = (n_profiles + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
   residual_kernel<<<(unsigned)blocks, 256, 0, stream>>>(vh, vh_obs, n_profiles, n_freq, residual, chi2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmin(const double* v, int64_t n, double* out2, cudaStream_t stream) {
+  argmin_kernel<<<1, 1024, 0, stream>>>(v, n, out2);
   return cudaGetLastError();
 }
 

@@ -107,6 +107,7 @@ cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, i
                           bool literal, double* mu, double* mup, cudaStream_t stream);
 cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
                             double* chi2, cudaStream_t stream);
+cudaError_t launch_argmin(const double* v, int64_t n, double* out2, cudaStream_t stream);
 // standalone stages (vfo_stages.cu)
 cudaError_t launch_den2freq(const double* den, int64_t n, double* out, int* negative_flag, cudaStream_t stream);
 cudaError_t launch_find_x(const double* den, int64_t den_stride, const double* f_hz, int64_t f_stride, int64_t n,

@@ -403,29 +403,6 @@ def residual_VH_batched(vh_obs, vh_model, *, return_residual=True):
     return (res.cpu().numpy() if res is not None else None), chi2.cpu().numpy()
 
 
-def brute_force_fit(freq, vh_obs, den_candidates, bmag, bpsi, alt, mode='O', n_points=200):
-    """Score a batch of candidate electron-density profiles against observed virtual heights.
-
-    What ``minimize_parameters`` (library.py:672-825) does per grid node of its brute-force search --
-    build a profile, run the forward operator, form the residual -- for ``den_candidates`` ``[P, A]`` supplied
-    by the caller (the PyIRI profile builder of library.py:557-583 is not available offline).  ``bmag`` /
-    ``bpsi`` are ``[A]`` (shared) or ``[P, A]``.  Returns ``(best_index, chi2 [P], vh_model [P, F])``; failed
-    candidates (negative density, peak at the bottom) score NaN.
-    """
-    den = _f64(den_candidates)
-    n_prof = den.shape[0]
-    bm = _f64(bmag)
-    bp = _f64(bpsi)
-    if bm.ndim == 1:
-        bm = np.ascontiguousarray(np.broadcast_to(bm, den.shape))
-    if bp.ndim == 1:
-        bp = np.ascontiguousarray(np.broadcast_to(bp, den.shape))
-    vh = vertical_forward_operator_batched(freq, den, bm, bp, alt, mode, n_points, errors='nan')
-    _, chi2 = residual_VH_batched(vh_obs, vh, return_residual=False)
-    best = int(np.nanargmin(chi2)) if np.isfinite(chi2).any() else -1
-    return best, chi2, vh
-
-
 _saved = {}
 
 

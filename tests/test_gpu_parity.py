@@ -399,22 +399,6 @@ def test_residual_objective(vfo):
     dev = torch.device("cuda:0")
     r2, c2 = vfo.residual_VH_batched(torch.from_numpy(vh_obs).to(dev), torch.from_numpy(vh).to(dev))
     assert np.array_equal(r2.cpu().numpy(), res, equal_nan=True) and np.array_equal(c2.cpu().numpy(), chi2, equal_nan=True)
-    # brute-force scoring: the candidate that generated the observations must win with chi2 == 0
-    alt = synth.default_alt()
-    freq = np.arange(2.0, 9.0, 0.25)
-    fof2 = np.linspace(8.0, 12.0, 9)
-    hmf2 = np.linspace(280.0, 340.0, 7)
-    ff, hh = np.meshgrid(fof2, hmf2, indexing="ij")
-    den, bmag, bpsi = synth.profiles_from_parameters(ff.ravel(), hh.ravel(), np.full(ff.size, 50.0),
-                                                     np.full(ff.size, 3.0), np.full(ff.size, 20.0), alt)
-    truth_idx = 31
-    obs = vfo.vertical_forward_operator(freq, den[truth_idx], bmag[truth_idx], bpsi[truth_idx], alt, 'O', 200)
-    assert np.all(np.isfinite(obs))
-    best, chi2, vh_all = vfo.brute_force_fit(freq, obs, den, bmag[0], bpsi[0], alt, 'O', 200)
-    assert best == truth_idx and chi2[truth_idx] == 0.0
-    assert vh_all.shape == (ff.size, freq.size)
-    ref_chi2 = np.sum(vfo_oracle.residual_from_model(obs, vh_all) ** 2, axis=1)
-    np.testing.assert_allclose(chi2, ref_chi2, rtol=1e-9, atol=1e-12)
 
 
 def test_config3_global_grid_full_size(vfo):
