@@ -13,8 +13,11 @@
  *   - units as the reference docstring (library.py:463-478): MHz, m^-3, Tesla, degrees, km.
  *   - mode: 0 = 'O', 1 = 'X' (library.py:391-396).
  *   - a prhf_ctx belongs to one CUDA device and caches the stretched-grid multiplier tables
- *     (one per n_points) plus a small workspace.  Calls on one ctx must be issued from one
- *     host thread / one stream at a time; create one ctx per stream for concurrency.
+ *     (one per n_points) plus a small workspace that serves ONE launch sequence at a time.  Calls on
+ *     one ctx must come from one host thread at a time; calls that arrive on different streams are
+ *     ordered on the device (the later stream waits for the earlier call), they do not overlap.
+ *     Create one ctx per host thread / per stream for concurrency (the Python package keeps one per
+ *     (device, thread)).
  *   - per-profile status (int32): 0 ok; 1 negative density below the peak (the reference raises
  *     ValueError, library.py:93-94); 2 density peak at index 0 (the reference raises IndexError at
  *     library.py:399).  Rows of a failed profile are NaN.
@@ -36,7 +39,8 @@ extern "C" {
 #define PRHF_ERR_INVALID_ARG 1    /* null pointer, negative size, n_points < 1 ...            */
 #define PRHF_ERR_BAD_MODE 2       /* mode not 0/1: ValueError("mode must be 'O' or 'X'")      */
 #define PRHF_ERR_CUDA 3           /* a CUDA runtime call failed; see prhf_last_cuda_error()   */
-#define PRHF_ERR_NALT_TOO_LARGE 4 /* n_alt exceeds the shared-memory staging limit            */
+#define PRHF_ERR_NALT_TOO_LARGE 4 /* n_alt exceeds the shared-memory staging limit (regrid stage and tracers \
+                                     only; the forward operator switches to a global-memory form) */
 #define PRHF_ERR_NO_DEVICE 5      /* no CUDA device / device is not sm_100                    */
 
 /* flags */
@@ -60,7 +64,9 @@ int prhf_last_cuda_error(const prhf_ctx* ctx, const char** text);
 int prhf_ctx_create(int device, prhf_ctx** out);
 void prhf_ctx_destroy(prhf_ctx* ctx);
 
-/* Largest n_alt the staging layout supports on this device. */
+/* Largest n_alt the shared-memory staging holds on this device (about 2 400 levels).  prhf_vfo_*_f64 accept longer
+ * profiles -- the reference has no limit (np.interp, library.py:424-426) -- through a slower form that keeps the
+ * levels in global memory; prhf_regrid_f64 and prhf_snell_f64 return PRHF_ERR_NALT_TOO_LARGE beyond it. */
 int prhf_max_n_alt(const prhf_ctx* ctx);
 
 /*

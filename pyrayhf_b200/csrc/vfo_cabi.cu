@@ -63,6 +63,8 @@ struct prhf_ctx {
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
+  void* node_table = nullptr;        // un-scaled nodes of profiles too long for shared memory (n_alt > prhf_max_n_alt)
+  size_t node_table_cap = 0;
   // optional per-kernel timing (bench roofline): events around K1 and K2 of every launch pair
   bool kernel_timing = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -245,7 +247,24 @@ int validate(const prhf_ctx* ctx, const void* freq, int n_freq, const void* den,
   if (n_freq < 0 || n_profiles < 0 || n_alt < 1 || n_points < 1) return PRHF_ERR_INVALID_ARG;
   if (n_freq == 0 || n_profiles == 0) return PRHF_OK;
   if (!freq || !den || !bmag || !bpsi || !alt || !vh) return PRHF_ERR_INVALID_ARG;
-  if (prhf::vfo_smem_bytes(n_alt) > (size_t)ctx->max_smem_optin) return PRHF_ERR_NALT_TOO_LARGE;
+  return PRHF_OK;
+}
+
+// More levels than the shared-memory staging holds: the operator switches to its global-memory form (no limit, as
+// np.interp has none, lib:424-426); the regrid stage and the tracers still stage in shared memory.
+bool too_long_for_smem(const prhf_ctx* ctx, int n_alt) {
+  return prhf::vfo_smem_bytes(n_alt) > (size_t)ctx->max_smem_optin;
+}
+
+int ensure_node_table(prhf_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->node_table_cap) return PRHF_OK;
+  PRHF_CUDA(ctx, cudaDeviceSynchronize());
+  if (ctx->node_table) cudaFree(ctx->node_table);
+  ctx->node_table = nullptr;
+  ctx->node_table_cap = 0;
+  PRHF_CUDA(ctx, cudaMalloc(&ctx->node_table, bytes));
+  ctx->node_table_cap = bytes;
+  ctx->epoch++;
   return PRHF_OK;
 }
 
@@ -324,6 +343,7 @@ void prhf_ctx_destroy(prhf_ctx* ctx) {
   if (ctx->counter) cudaFree(ctx->counter);
   if (ctx->live_count) cudaFree(ctx->live_count);
   if (ctx->live_list) cudaFree(ctx->live_list);
+  if (ctx->node_table) cudaFree(ctx->node_table);
   if (ctx->prof_rec) cudaFree(ctx->prof_rec);
   if (ctx->row_span) cudaFree(ctx->row_span);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
@@ -408,7 +428,13 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
 
   const int64_t rows_total = n_profiles * (int64_t)n_freq;
   const bool literal = (flags & PRHF_FLAG_LITERAL) != 0;
-  const CallMode cm = call_mode(ctx, rows_total, n_points, n_alt);
+  const bool big = too_long_for_smem(ctx, n_alt);             // global-memory form: direct mode only
+  CallMode cm = call_mode(ctx, rows_total, n_points, big ? 1 : n_alt);
+  if (big) {
+    cm.solo = cm.planned = false;
+    cm.ctas_per_sm = prhf::kTileMinBlocks;
+    cm.slots = ctx->sm_count * cm.ctas_per_sm;
+  }
   const int ctas_per_sm = cm.ctas_per_sm, slots = cm.slots;
 
   // Small batches (fewer rows than a few waves of tiles): planned mode.  K1's last CTA counts the rows
@@ -450,6 +476,9 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
   const int64_t tiles_per_profile = (int64_t)n_freq * n_seg;
   if (tiles_per_profile > max_tiles) return PRHF_ERR_INVALID_ARG;
   int64_t prof_per_launch = std::max<int64_t>(1, std::min(max_tiles / tiles_per_profile, max_rows / n_freq));
+  if (big)                                                    // node table of one launch: at most 512 MiB
+    prof_per_launch = std::max<int64_t>(1, std::min<int64_t>(prof_per_launch,
+                                                             (int64_t)(((size_t)512 << 20) / (prhf::vfo_node_bytes() * (size_t)n_alt))));
   prof_per_launch = std::min(prof_per_launch, n_profiles);
   const int64_t rows_launch = prof_per_launch * n_freq;
   rc = ensure_records(ctx, (size_t)prof_per_launch, (size_t)rows_launch);
@@ -460,6 +489,10 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
   }
   if (planned) {
     rc = ensure_plan(ctx, (size_t)rows_launch);
+    if (rc != PRHF_OK) return rc;
+  }
+  if (big) {
+    rc = ensure_node_table(ctx, prhf::vfo_node_bytes() * (size_t)n_alt * (size_t)prof_per_launch);
     if (rc != PRHF_OK) return rc;
   }
   // K1 granularity: 8 rows per CTA while the launch is small (latency matters), whole profiles per CTA
@@ -523,6 +556,31 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.trace_k1 = ctx->trace ? ctx->trace + ctx->trace_k1_off : nullptr;
     P.freq_scale = 1e6;                                       // lib:491
     P.row_hc = nullptr;
+    P.levels_in_global = big ? 1 : 0;
+    P.node_table = ctx->node_table;
+    if (big) {
+      // row setup (thread per frequency, levels read in place) -> node table -> tiles; plain stream order
+      P.use_pdl = 0;
+      P.k1_lane_mode = 1;
+      const bool timing = ctx->kernel_timing;
+      if (timing) PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_nodes_global(P, literal, np, stream));
+      if (timing) PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+      PRHF_CUDA(ctx, prhf::launch_vfo_tiles_global(P, mode, literal, np * tiles_per_profile, stream));
+      ctx->launches += 3;
+      if (timing) {
+        PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+        PRHF_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        ctx->k1_ms += a;
+        ctx->k2_ms += b;
+        ctx->timed_pairs++;
+      }
+      continue;
+    }
     if (solo) {
       if (ctx->kernel_timing) PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
       PRHF_CUDA(ctx, prhf::launch_vfo_solo(P, mode, literal, np * tiles_per_profile, stream));
@@ -1081,6 +1139,7 @@ int prhf_regrid_f64(prhf_ctx* ctx, const double* f_hz, int n_freq, const double*
   int rc = validate(ctx, f_hz, n_freq, n_e, b, bpsi, aalt, 1, n_alt, mode, n_points, crit_height);
   if (rc != PRHF_OK) return rc;
   if (n_freq == 0) return PRHF_OK;
+  if (too_long_for_smem(ctx, n_alt)) return PRHF_ERR_NALT_TOO_LARGE;   // this stage stages the profile in shared memory
   if (n_freq > 65535) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   cudaStream_t stream = (cudaStream_t)cuda_stream;

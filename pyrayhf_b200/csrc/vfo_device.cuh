@@ -259,10 +259,13 @@ constexpr double kSmallRotateStep = 4e-4;
 
 // ---- numpy arr_interp for one query against the staged altitude axis (left = fp[0], right = fp[n-1]) ----
 // Returns the bracket: -2 NaN query, -1 below the axis, n above it, else the last j with xp[j] <= x.
+// The two range tests come first and in numpy's order (binary_search_with_guess: "key > arr[len - 1]" before
+// "key < arr[0]"), which is what defines np.interp on a DEcreasing axis: every query above the last (smallest)
+// coordinate takes the right-hand fill value fp[n-1], whatever lies in between.
 __device__ __forceinline__ int np_bracket(double x, const double* __restrict__ xp, int n) {
   if (x != x) return -2;
-  if (x < xp[0]) return -1;
   if (x > xp[n - 1]) return n;
+  if (x < xp[0]) return -1;
   int lo = 0, hi = n - 1;                                   // xp[lo] <= x <= xp[hi]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;

@@ -343,14 +343,17 @@ __device__ __noinline__ double dead_row_single_level(int mode, bool iso, double 
 __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, const int64_t item, double* smem,
                                           BlockScratch& sc, ProfileRecord* s_rec, double* s_span) {
   const int A = p.n_alt;
-  double* s_den = smem;
-  double* s_alt = s_den + A;
-  double* s_b = s_alt + A;
-  double* s_psi = s_b + A;
-  double* s_crit = s_psi + A;    // [kRowsPerCta][A]
+  // levels staged in shared memory -- or, for profiles with more levels than it holds (p.levels_in_global; the host
+  // then always asks for the thread-per-frequency mapping, which needs no per-warp scratch), read in place
+  const bool glob = p.levels_in_global != 0;
+  double* w_den = smem;
+  double* w_alt = w_den + A;
+  double* w_b = w_alt + A;
+  double* w_psi = w_b + A;
+  double* s_crit = w_psi + A;    // [kRowsPerCta][A]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int rows_per_cta = p.k1_solo ? 1 : (p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp);
+  const int rows_per_cta = p.k1_solo ? 1 : ((p.k1_lane_mode || p.levels_in_global) ? kThreads : kRowsPerCta * p.rows_per_warp);
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   const int64_t lprof = item / chunks;                  // profile index inside this launch
   const int g = (int)(item % chunks);
@@ -360,6 +363,10 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   const double* g_b = p.bmag + prof * A;
   const double* g_psi = p.bpsi + prof * A;
   const double* g_alt = p.alt + prof * p.alt_stride;
+  const double* s_den = glob ? g_den : w_den;
+  const double* s_alt = glob ? g_alt : w_alt;
+  const double* s_b = glob ? g_b : w_b;
+  const double* s_psi = glob ? g_psi : w_psi;
 
   PRHF_TRACE_K1(0);
 #ifdef PRHF_TRACE
@@ -384,20 +391,24 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     for (int u = 0; u < kPre; ++u) {
       const int k = tid + u * kThreads;
       if (k < A) {
-        s_den[k] = d[u];
-        s_alt[k] = a[u];
-        s_b[k] = b[u];
-        s_psi[k] = ps[u];
+        if (!glob) {
+          w_den[k] = d[u];
+          w_alt[k] = a[u];
+          w_b[k] = b[u];
+          w_psi[k] = ps[u];
+        }
         if (arg_precedes(d[u], k, best_v, best_i)) { best_v = d[u]; best_i = k; }
         amin = fmin(amin, a[u]);
       }
     }
     for (int k = tid + kPre * kThreads; k < A; k += kThreads) {
       const double dk = g_den[k], ak = g_alt[k], bk = g_b[k], pk = g_psi[k];
-      s_den[k] = dk;
-      s_alt[k] = ak;
-      s_b[k] = bk;
-      s_psi[k] = pk;
+      if (!glob) {
+        w_den[k] = dk;
+        w_alt[k] = ak;
+        w_b[k] = bk;
+        w_psi[k] = pk;
+      }
       if (arg_precedes(dk, k, best_v, best_i)) { best_v = dk; best_i = k; }
       amin = fmin(amin, ak);
     }
@@ -429,7 +440,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     if (!(fabs(a - fma((double)k, mean_step, alt0)) <= 2e-15 * fmax(fabs(a), mean_step))) chk |= 4;   // ~8 ulp
     if (!(a > 0.0)) chk |= 2;                           // the fast paths compare altitudes as integers
     if (k + 1 < nt) {
-      if (!(__dsub_rn(s_alt[k + 1], a) > 0.0)) chk |= 2;
+      if (!(__dsub_rn(s_alt[k + 1], a) > 0.0)) chk |= 2 | 8;   // not strictly increasing: general path, np.interp range tests
       const double step = fabs(__dsub_rn(s_psi[k + 1], ps)) * kDeg2Rad;
       if (!(step <= kMaxRotateStep)) chk |= 2;
       step_max = fmax(step_max, step);
@@ -465,7 +476,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     rec.nt = nt;
     rec.flags = (iso ? kFlagIso : 0) | (any_general ? kFlagGeneral : 0) | (status ? kFlagFailed : 0) |
                 (step_max == 0.0 ? kFlagPsiConst : 0) | (step_max <= kSmallRotateStep ? kFlagPsiSmall : 0) |
-                (any_nonuniform ? 0 : kFlagUniformAlt);
+                (any_nonuniform ? 0 : kFlagUniformAlt) | ((r2.flags & 8) ? kFlagAltUnsorted : 0);
     rec.alt_min = alt_min;
     rec.inv_dalt = (nt > 1) ? (double)(nt - 1) * rcp_fast(s_alt[nt - 1] - alt0) : 0.0;
     rec.alt0 = alt0;
@@ -485,7 +496,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
   // (cand) and the largest screen value below it (kmax) with its runner-up; pass B evaluates those two
   // levels literally.  Rows where the screen cannot separate the candidates (values within kScreenTol of a
   // decision, or a literal candidate that turns out <= 1) fall back to a sequential literal scan.
-  if (p.k1_lane_mode) {
+  if (p.k1_lane_mode || glob) {
     const int r = g * kThreads + tid;
     if (r >= p.n_freq) return;
     const int64_t out_idx = prof * p.n_freq + r;
@@ -779,7 +790,20 @@ struct RowConst {
   double kx, ky;    // cp^2/f^2 and g_p/f, applied per point when the staged nodes are not pre-scaled
   const double* g_alt;   // the profile's raw altitude / density levels: O-mode points next to the reflection level
   const double* g_den;   // re-evaluate X in numpy's operation order (near_reflection_tail)
+  int unsorted;          // altitudes below the peak are not strictly increasing (kFlagAltUnsorted)
 };
+
+// np.interp on an axis that is not increasing.  What numpy does is decided by the two range tests that precede its
+// search (binary_search_with_guess: key > arr[len-1] -> right fill value, else key < arr[0] -> left fill value); on a
+// strictly DEcreasing grid one of them always fires, so every interpolant is fp[len-1] (or fp[0] at/below the smallest
+// altitude) -- e.g. Day profile, reversed arrays: 4 finite virtual heights of 174 (tests/golden/edge.npz).  Inside the
+// range of a zig-zag axis numpy's result depends on the guess it carries from query to query; a plain bisection
+// stands in there (documented as undefined, as numpy documents it).  `nodes` holds all levels [0, nt).
+__device__ __forceinline__ int bracket_unsorted(double h, const Node* nodes, int nt) {
+  if (h > nodes[nt - 1].alt) return nt - 1;
+  if (h < nodes[0].alt) return -1;
+  return max(bracket_in<8>(h, &nodes[0].alt, 0, nt - 1), 0);
+}
 
 // Bracket of h inside the staged window: last j in [jlo, jhi] with alt[j] <= h (jlo - 1 if below).
 // `guess` is tried first (exact for uniform grids up to rounding), then its neighbours, then bisection.
@@ -886,9 +910,15 @@ __device__ __forceinline__ double tile_sum(const Node* nodes, const RowConst& rc
       t0 = mup0 * dh0;
       t1 = mup0 * dh1;
     } else {
-      const int g0 = __double2int_rd((h0 - rc.alt0) * rc.inv_dalt);
-      int j0 = find_bracket(h0, nodes, rc.jlo, rc.jhi, g0);
-      int j1 = find_bracket(h1, nodes, rc.jlo, rc.jhi, j0);
+      int j0, j1;
+      if (rc.unsorted) {
+        j0 = bracket_unsorted(h0, nodes, rc.nt);
+        j1 = bracket_unsorted(h1, nodes, rc.nt);
+      } else {
+        const int g0 = __double2int_rd((h0 - rc.alt0) * rc.inv_dalt);
+        j0 = find_bracket(h0, nodes, rc.jlo, rc.jhi, g0);
+        j1 = find_bracket(h1, nodes, rc.jlo, rc.jhi, j0);
+      }
       t0 = point_term<MODE, PATH>(h0, dh0, j0, nodes, rc);
       t1 = point_term<MODE, PATH>(h1, dh1, j1, nodes, rc);
     }
@@ -1204,6 +1234,43 @@ __device__ __forceinline__ ProfileRecord load_profile_record(const ProfileRecord
   return u.r;
 }
 
+// Evaluation path of a profile from the flags the row setup recorded.
+template <bool LITERAL>
+__device__ __forceinline__ int select_path(int flags) {
+  if (flags & kFlagIso) return kPathIso;
+  if (LITERAL) return kPathLiteral;
+  if (flags & kFlagGeneral) return kPathGeneral;
+  if (flags & kFlagPsiConst) return kPathFast0;
+  if (flags & kFlagPsiSmall) return kPathFastS;
+  return kPathFastL;
+}
+
+// Block reduction of a tile's share, combination of the segments of a row, lib:288-292.
+__device__ __forceinline__ void finish_tile(const VfoParams& p, BlockScratch& sc, double acc, int64_t lrow, int seg,
+                                            int n_seg, int64_t out_idx, double alt_min) {
+  PRHF_TRACE_MARK(6);
+  const double s_tile = block_sum(acc, sc);
+  PRHF_TRACE_MARK(7);
+#ifdef PRHF_TRACE
+  if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + 0] |= (trace_globaltimer() << 10);
+#endif
+  if (threadIdx.x != 0) return;
+  double total = s_tile;
+  if (n_seg > 1) {
+    double* part = p.partial + lrow * p.max_seg;
+    __stcg(part + seg, s_tile);
+    __threadfence();
+    const unsigned prev = atomicAdd(p.counter + lrow, 1u);
+    if (prev != (unsigned)(n_seg - 1)) return;
+    __threadfence();
+    total = 0.0;
+    for (int s = 0; s < n_seg; ++s) total += __ldcg(part + s);     // fixed order: deterministic
+    p.counter[lrow] = 0u;                                 // self-reset for the next launch
+  }
+  if (total == 0.0) total = CUDART_NAN;                   // lib:290
+  p.vh[out_idx] = total + alt_min;                        // lib:292
+}
+
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
@@ -1233,13 +1300,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   PRHF_TRACE_MARK(3);
   const int nt = rec.nt;
 
-  int path;
-  if (rec.flags & kFlagIso) path = kPathIso;
-  else if (LITERAL) path = kPathLiteral;
-  else if (rec.flags & kFlagGeneral) path = kPathGeneral;
-  else if (rec.flags & kFlagPsiConst) path = kPathFast0;
-  else if (rec.flags & kFlagPsiSmall) path = kPathFastS;
-  else path = kPathFastL;
+  const int path = select_path<LITERAL>(rec.flags);
   const int A = p.n_alt;
   const double* g_den = p.den + prof * A;
   const double* g_b = p.bmag + prof * A;
@@ -1256,12 +1317,17 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   rc.nt = nt;
   double kx, ky;                                          // fast paths: X = den * kx, Y = b * ky
   row_scales(rc.f_hz, &kx, &ky);
-  const bool const_mup = !(span > 0.0) || nt == 1;         // h_c <= alt0: every point clamps to level 0
+  const bool unsorted = (rec.flags & kFlagAltUnsorted) != 0;
+  rc.unsorted = unsorted ? 1 : 0;
+  const bool const_mup = (!(span > 0.0) || nt == 1) && !unsorted;   // h_c <= alt0: every point clamps to level 0
   PRHF_TRACE_X(10);
 
   // ---- node window of this tile: brackets of its first and last grid point ----
   if (const_mup) {
     rc.jlo = rc.jhi = 0;
+  } else if (unsorted) {
+    rc.jlo = 0;                                           // np.interp's range tests need both ends of the axis
+    rc.jhi = nt - 1;
   } else {
     const double h_lo = __dadd_rn(__dmul_rn(m_lo, span), rc.alt0);
     const double h_hi = __dadd_rn(__dmul_rn(m_hi, span), rc.alt0);
@@ -1302,27 +1368,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
                                                       p.mult, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
-  PRHF_TRACE_MARK(6);
-  const double s_tile = block_sum(acc, sc);
-  PRHF_TRACE_MARK(7);
-#ifdef PRHF_TRACE
-  if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 8 + 0] |= (trace_globaltimer() << 10);
-#endif
-  if (tid != 0) return;
-  double total = s_tile;
-  if (n_seg > 1) {
-    double* part = p.partial + lrow * p.max_seg;
-    __stcg(part + seg, s_tile);
-    __threadfence();
-    const unsigned prev = atomicAdd(p.counter + lrow, 1u);
-    if (prev != (unsigned)(n_seg - 1)) return;
-    __threadfence();
-    total = 0.0;
-    for (int s = 0; s < n_seg; ++s) total += __ldcg(part + s);     // fixed order: deterministic
-    p.counter[lrow] = 0u;                                 // self-reset for the next launch
-  }
-  if (total == 0.0) total = CUDART_NAN;                   // lib:290
-  p.vh[prof * p.n_freq + r] = total + rec.alt_min;        // lib:292
+  finish_tile(p, sc, acc, lrow, seg, n_seg, prof * p.n_freq + r, rec.alt_min);
 }
 
 // Direct mode (large batches): tile = blockIdx.x, n_seg fixed by the host; rows without reflection exit.
@@ -1407,13 +1453,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
   if (!__syncthreads_or(live)) return;
 
   const int nt = rec.nt;
-  int path;
-  if (rec.flags & kFlagIso) path = kPathIso;
-  else if (LITERAL) path = kPathLiteral;
-  else if (rec.flags & kFlagGeneral) path = kPathGeneral;
-  else if (rec.flags & kFlagPsiConst) path = kPathFast0;
-  else if (rec.flags & kFlagPsiSmall) path = kPathFastS;
-  else path = kPathFastL;
+  const int path = select_path<LITERAL>(rec.flags);
+  const bool unsorted = (rec.flags & kFlagAltUnsorted) != 0;
 
   const int A = p.n_alt;
   const double* g_den = p.den + prof * A;
@@ -1440,7 +1481,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
     row_scales(rc.f_hz, &rc.kx, &rc.ky);
     rc.lane0 = lane;
     rc.group = 32;
-    const bool const_mup = !(span > 0.0) || nt == 1;       // h_c <= alt0: every point clamps to level 0
+    rc.unsorted = unsorted ? 1 : 0;
+    const bool const_mup = (!(span > 0.0) || nt == 1) && !unsorted;   // h_c <= alt0: every point clamps to level 0
     rc.jlo = 0;
     rc.jhi = const_mup ? 0 : nt - 1;
     double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, p.mult, 0,
@@ -1451,6 +1493,62 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
       p.vh[prof * p.n_freq + r] = acc + rec.alt_min;      // lib:292
     }
   }
+}
+
+// ---- profiles with more levels than the shared-memory staging holds (n_alt > prhf_max_n_alt()) ----
+// The reference has no such limit (np.interp, lib:424-426).  Row setup: the thread-per-frequency mapping reading the
+// levels in place (rows_body, p.levels_in_global).  Then one CTA per profile writes the profile's UN-scaled nodes
+// (np.interp slopes, sin/cos of the field angle) to a table in global memory, and the tile kernel below reads them
+// through L1/L2 with the row's cp^2/f^2 and g_p/f applied per point -- the arithmetic of the row-per-warp kernel with
+// a CTA per tile.  Slower per point than the staged form (two more FP64 multiplies, table reads instead of shared
+// memory), but every decision and every value is the same.
+template <bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads) vfo_nodes_global_kernel(const VfoParams p) {
+  const int64_t lprof = blockIdx.x;
+  const int64_t prof = p.profile_offset + lprof;
+  const ProfileRecord rec = p.prof_rec[lprof];
+  if (rec.flags & kFlagFailed) return;
+  const int A = p.n_alt;
+  Node* nodes = reinterpret_cast<Node*>(p.node_table) + lprof * A;
+  stage_nodes(nodes, 0, rec.nt, rec.nt, select_path<LITERAL>(rec.flags), rec, p.alt + prof * p.alt_stride,
+              p.den + prof * A, p.bmag + prof * A, p.bpsi + prof * A, 1.0, 1.0, threadIdx.x, kTileThreads);
+}
+
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_global_kernel(const VfoParams p) {
+  __shared__ BlockScratch sc;
+  const unsigned tile = blockIdx.x;
+  const unsigned lrow = (p.n_seg == 1) ? tile : tile / (unsigned)p.n_seg;
+  const int seg = (p.n_seg == 1) ? 0 : (int)(tile - lrow * (unsigned)p.n_seg);
+  const double span = p.row_span[lrow];
+  if (!(span == span)) return;                            // no reflection / failed profile: the row setup wrote the NaN
+  const unsigned lprof = lrow / (unsigned)p.n_freq;
+  const int r = (int)(lrow - lprof * (unsigned)p.n_freq);
+  const int64_t prof = p.profile_offset + lprof;
+  const ProfileRecord rec = p.prof_rec[lprof];
+  const int A = p.n_alt, nt = rec.nt;
+  const int path = select_path<LITERAL>(rec.flags);
+  const double* g_den = p.den + prof * A;
+  RowConst rc;
+  rc.g_alt = p.alt + prof * p.alt_stride;
+  rc.g_den = g_den;
+  rc.f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], 1e6);
+  rc.alt0 = rec.alt0;
+  rc.span = span;
+  rc.inv_dalt = rec.inv_dalt;
+  rc.nt = nt;
+  row_scales(rc.f_hz, &rc.kx, &rc.ky);
+  rc.lane0 = threadIdx.x;
+  rc.group = kTileThreads;
+  rc.unsorted = (rec.flags & kFlagAltUnsorted) ? 1 : 0;
+  const bool const_mup = (!(span > 0.0) || nt == 1) && !rc.unsorted;
+  rc.jlo = 0;
+  rc.jhi = const_mup ? 0 : nt - 1;
+  const int i0 = seg * p.seg_len, i1 = min(p.n_points, i0 + p.seg_len);
+  const Node* nodes = reinterpret_cast<const Node*>(p.node_table) + (size_t)lprof * A;
+  const double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, g_den[0],
+                                                     p.bmag[prof * A], p.bpsi[prof * A], p.mult, i0, i1, p.n_points);
+  finish_tile(p, sc, acc, lrow, seg, p.n_seg, prof * p.n_freq + r, rec.alt_min);
 }
 
 // Solo form for a single profile (rows * n_seg <= resident CTAs): ONE launch, no hand-off through global
@@ -1660,11 +1758,31 @@ static cudaError_t grant_dynamic_smem(const void* func, int slot, size_t smem) {
   return e;
 }
 
+size_t vfo_node_bytes() { return sizeof(Node); }
+
+cudaError_t launch_vfo_nodes_global(const VfoParams& p, bool literal, int64_t n_profiles, cudaStream_t stream) {
+  if (literal) vfo_nodes_global_kernel<true><<<(unsigned)n_profiles, kTileThreads, 0, stream>>>(p);
+  else vfo_nodes_global_kernel<false><<<(unsigned)n_profiles, kTileThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream) {
+  const unsigned g = (unsigned)n_tiles;
+  if (mode == 0) {
+    if (literal) vfo_tile_global_kernel<0, true><<<g, kTileThreads, 0, stream>>>(p);
+    else vfo_tile_global_kernel<0, false><<<g, kTileThreads, 0, stream>>>(p);
+  } else {
+    if (literal) vfo_tile_global_kernel<1, true><<<g, kTileThreads, 0, stream>>>(p);
+    else vfo_tile_global_kernel<1, false><<<g, kTileThreads, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream) {
-  const size_t smem = vfo_rows_smem_bytes(p.n_alt);
+  const size_t smem = p.levels_in_global ? 0 : vfo_rows_smem_bytes(p.n_alt);
   cudaError_t e = grant_dynamic_smem((const void*)vfo_rows_kernel, 0, smem);
   if (e != cudaSuccess) return e;
-  const int rows_per_cta = p.k1_lane_mode ? kThreads : kRowsPerCta * p.rows_per_warp;
+  const int rows_per_cta = (p.k1_lane_mode || p.levels_in_global) ? kThreads : kRowsPerCta * p.rows_per_warp;
   const int chunks = (p.n_freq + rows_per_cta - 1) / rows_per_cta;
   vfo_rows_kernel<<<(unsigned)(n_profiles * chunks), kThreads, smem, stream>>>(p, mode);
   return cudaGetLastError();

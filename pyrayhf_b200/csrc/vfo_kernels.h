@@ -28,6 +28,7 @@ constexpr int kFlagFailed = 4;    // status != 0
 constexpr int kFlagPsiConst = 8;  // field angle identical at every level below the peak
 constexpr int kFlagPsiSmall = 16; // per-level field-angle steps <= kSmallRotateStep
 constexpr int kFlagUniformAlt = 32; // levels within a quarter step of alt0 + k * mean step: the bracket guess is exact +-1
+constexpr int kFlagAltUnsorted = 64; // altitudes below the peak not strictly increasing: np.interp's range tests decide
 
 struct __align__(16) ProfileRecord {  // 64 bytes per profile, written by K1, read by K2
   int nt;                         // truncated length = argmax(den) (lib:371)
@@ -88,6 +89,10 @@ struct VfoParams {
   double freq_scale;       // row setup: f_hz = freq * freq_scale (1e6 for MHz input, lib:491; 1 for the Hz input of
                            // the standalone regrid stage).  The tile kernels always assume MHz.
   double* row_hc;          // optional [rows_in_launch]: reflection height h_c (lib:407), NaN on rows without one
+  // profiles with more levels than the shared-memory staging holds (n_alt > prhf_max_n_alt): the row setup reads the
+  // levels straight from global memory and the tile kernel reads un-scaled nodes from this per-profile table
+  int levels_in_global;
+  void* node_table;        // Node[profiles_in_launch x n_alt]
   // Kernel parameters sit in a constant bank that is cold at every launch; each 128-byte line of this struct costs
   // its first reader a miss.  Everything the single-profile path touches stays above this comment (two lines);
   // the planner's candidate tables (256 bytes, planned mode only) come last.
@@ -102,6 +107,9 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
 cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
+size_t vfo_node_bytes();
+cudaError_t launch_vfo_nodes_global(const VfoParams& p, bool literal, int64_t n_profiles, cudaStream_t stream);
+cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
