@@ -45,7 +45,7 @@ BASE_PROFILES = 8192          # perturbed profiles per member (BASELINE.json con
 N_PROFILES = MEMBERS * BASE_PROFILES
 LAYOUT = "interleaved"
 FLOPS_PER_POINT = 77          # algorithmic FP64 operations per grid point of a row that reflects
-FLOPS_PER_CLAMPED_POINT = 2   # rows that reflect at/below the first level: one subtraction + one FMA per point
+FLOPS_PER_CLAMPED_ROW = 77    # rows that reflect at/below the first level: ONE evaluation of mu' (the weights telescope)
 
 
 def load_synth():
@@ -273,10 +273,9 @@ def row_classes(torch, freq_mhz, den, bmag, mode):
 
 
 def algorithmic_flops(n_loop, n_clamp, at_sum, n_points):
-    """W: 77 N + 8 per row that enters the grid loop, 2 N + 8 per row clamped to the first level,
-    4 per truncated level of EVERY row (critical curve)."""
-    return (n_loop * (FLOPS_PER_POINT * n_points + 8) + n_clamp * (FLOPS_PER_CLAMPED_POINT * n_points + 8) +
-            4 * at_sum)
+    """W: 77 N + 8 per row that enters the grid loop, 77 + 8 per row clamped to the first level
+    (constant mu': one evaluation, the weights telescope), 4 per truncated level of EVERY row (critical curve)."""
+    return n_loop * (FLOPS_PER_POINT * n_points + 8) + n_clamp * (FLOPS_PER_CLAMPED_ROW + 8) + 4 * at_sum
 
 
 def timed(torch, stream, fn, reps=5, warm=2, flush=None):
@@ -660,8 +659,8 @@ def run_b200_arm(args):
                      "launches_per_step_per_rank": launches_per_step,
                      "step_frac": (flops_shard / (total_ms / args.steps * 1e-3) / 1e12) / peak_tf,
                      "algorithmic_flops_per_launch": flops_launch,
-                     "note": "achieved = W (77 flop per grid point of a row that enters the grid loop, 2 per point of "
-                             "a row clamped to the first level, 4 per truncated level of every row; SURVEY 8d) of one "
+                     "note": "achieved = W (77 flop per grid point of a row that enters the grid loop, 77 per row "
+                             "clamped to the first level, 4 per truncated level of every row; SURVEY 8d) of one "
                              "launch / its duration from CUDA events on its stream (prhf_kernel_timing); step_frac "
                              "uses rank 0's whole timed step (row setup, copies and barrier included)",
                      "peak_source": "prhf_measure_fp64_peak: dependent-free DFMA kernel timed live on this GPU "

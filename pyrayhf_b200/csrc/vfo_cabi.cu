@@ -124,9 +124,10 @@ int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const doubl
     return PRHF_OK;
   }
   double* m = nullptr;
-  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * ((size_t)n_points + prhf::kMultPad)));
-  cudaError_t e = prhf::launch_grid_multiplier(n_points, m, stream);
-  ctx->launches++;
+  const size_t len = prhf::mult_table_len(n_points);          // [m | dm], dm = m + len
+  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * 2 * len));
+  cudaError_t e = prhf::launch_grid_multiplier(n_points, len, m, m + len, stream);
+  ctx->launches += 2;
   if (e != cudaSuccess) {
     cudaFree(m);
     return fail(ctx, e);
@@ -406,7 +407,7 @@ int prhf_debug_trace_read(prhf_ctx* ctx, int64_t n_tiles, long long* out) {
 int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* cuda_stream) {
   if (!ctx || n_points < 1 || !m_out) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
-  PRHF_CUDA(ctx, prhf::launch_grid_multiplier(n_points, m_out, (cudaStream_t)cuda_stream));
+  PRHF_CUDA(ctx, prhf::launch_grid_multiplier(n_points, (size_t)n_points, m_out, nullptr, (cudaStream_t)cuda_stream));
   ctx->launches++;
   return PRHF_OK;
 }
@@ -517,6 +518,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.n_alt = n_alt;
     P.profile_offset = p0;
     P.mult = mult;
+    P.dmult = mult + prhf::mult_table_len(n_points);
     P.n_points = n_points;
     P.seg_len = seg_len;
     P.n_seg = n_seg;
@@ -1158,6 +1160,7 @@ int prhf_regrid_f64(prhf_ctx* ctx, const double* f_hz, int n_freq, const double*
   P.alt = aalt;
   P.n_alt = n_alt;
   P.mult = mult;
+  P.dmult = mult + prhf::mult_table_len(n_points);
   P.n_points = n_points;
   P.seg_len = n_points;
   P.n_seg = 1;

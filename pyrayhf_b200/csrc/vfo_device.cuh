@@ -86,11 +86,14 @@ __device__ __forceinline__ double rcp_fast(double x) {
   const double e = fma(-x, y, 1.0);
   return fma(y, fma(e, e, e), y);                      // y (1 + e + e^2)
 }
+// (3/8 comes from the constant bank: fma(e, 0.375, 0.5) holds two literals and only one fits the instruction, so the
+//  compiler would otherwise rebuild 0.375 in a register pair inside every loop that is short of registers.)
+static __constant__ double kThreeEighths = 0.375;
 __device__ __forceinline__ double rsqrt_fast(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double e = fma(-(x * y), y, 1.0);              // 1 - x y^2
-  return fma(y, e * fma(e, 0.375, 0.5), y);            // y (1 + e/2 + 3 e^2 / 8)
+  return fma(y, e * fma(e, kThreeEighths, 0.5), y);    // y (1 + e/2 + 3 e^2 / 8)
 }
 
 // ---- per-row scale factors of the screen and the fast paths: X = den * kx, Y = b * ky ----
@@ -184,7 +187,7 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
   const double beta = alpha * rb;
   const double P = a + beta;
   const double T = fma(a2, rb, beta);                   // beta + a^2 / beta
-  double mu, c, q, dDdX, hYd;                           // hYd = (Y dD/dY) / 2
+  double mu, nc, q, dDdX, hYd;                          // nc = -1/(D mu), hYd = (Y dD/dY) / 2
   if (MODE == 1) {
     const double D = Xm1 - P;
     const double XX = X * Xm1;
@@ -193,7 +196,9 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
     const double t1 = E * rs;
     mu = fabs(t1);
     q = XX * (t1 * rs);
-    c = copysign(rs, t1);
+    // nc = -copysign(rs, t1) = -1/(D mu), sign bit assembled with ONE integer instruction (rs > 0 or NaN): written
+    // as copysign + negation the compiler negates t1 on the FP64 pipe first
+    nc = __hiloint2double(__double2hiint(rs) | (~__double2hiint(t1) & (int)0x80000000), __double2loint(rs));
     dDdX = fma(w, rb, -1.0);
     hYd = fma(-0.5, T, -a);
   } else {
@@ -204,14 +209,15 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
     const double v = z * rs;
     mu = fabs(v);
     q = (X * P) * (v * (Xm1 * rs));
-    c = P * rs;
+    nc = -(P * rs);
     dDdX = -fma(w, rb, 1.0);
     hYd = fma(0.5, T, -a);
   }
-  const double br = fma(q, hYd, X * fma(q, dDdX, fma(2.0, X, -1.0)));
+  // 2X - 1 as X - (1 - X): one addition without a literal (fma(2.0, X, -1.0) needs 2.0 in a register pair)
+  const double br = fma(q, hYd, X * fma(q, dDdX, X - Xm1));
   *mu_out = mu;
   *q_out = q;
-  return fma(-c, br, mu);
+  return fma(nc, br, mu);
 }
 
 // mu' is kept when the reference keeps it: mu not NaN (lib:233), mu <= 1 (lib:238), mu' itself not NaN
@@ -227,6 +233,20 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
 //   mu' finite               <=>  hi(|mu'|) < 0x7FF00000
 // A NaN mu (lib:233: D E < 0 under the reciprocal square root) makes mu' NaN, so mu needs no test of its own; an
 // infinite mu' cannot come out of ah_hot (mu == 0 gives 0 * inf = NaN there).
+// acc += mu' * w when keep_term holds: the two integer tests feed the predicate of ONE predicated DFMA (as a select
+// the compiler spends four FSEL per grid point on the two halves of the operand).
+__device__ __forceinline__ void add_kept(double& acc, double mup, double q, double w) {
+  asm("{\n\t"
+      ".reg .pred k1, k2;\n\t"
+      ".reg .u32 ph;\n\t"
+      "and.b32 ph, %3, 0x7fffffff;\n\t"
+      "setp.lt.u32 k1, ph, 0x7ff00000;\n\t"
+      "setp.lt.and.u32 k2, %4, 0xBCA80000, k1;\n\t"
+      "@k2 fma.rn.f64 %0, %1, %2, %0;\n\t"
+      "}"
+      : "+d"(acc)
+      : "d"(mup), "d"(w), "r"(__double2hiint(mup)), "r"(__double2hiint(q)));
+}
 __device__ __forceinline__ bool keep_term(double mup, double q) {
   const unsigned ph = (unsigned)__double2hiint(mup) & 0x7fffffffu;
   const unsigned qh = (unsigned)__double2hiint(q);

@@ -61,6 +61,15 @@ __device__ __forceinline__ int trace_smid() {
 // The table has kMultPad extra entries (copies of the last entry) so that the main loop can read m[i+1],
 // m[i+2] unconditionally and the row's last point gets the in-loop weight h(pad) - h(last) = 0.
 // ------------------------------------------------------------------------------------------
+// dm_i = m_{i+1} - m_i: the weight of grid point i in units of the row's span (lib:415: dh_i = h_{i+1} - h_i with
+// h = m (h_c - alt0) + alt0, lib:413); 0 from the row's last point on (that point weighs 1e-6 km, lib:416, added by
+// its owner after the loop).
+__global__ void grid_dmult_kernel(int n, int n_padded, const double* __restrict__ m, double* __restrict__ dm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_padded) return;
+  dm[i] = (i < n - 1) ? __dsub_rn(m[i + 1], m[i]) : 0.0;
+}
+
 __global__ void grid_multiplier_kernel(int n, int n_padded, double step, double* __restrict__ m) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded) return;
@@ -951,10 +960,11 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
 // ROWSCALE: the staged nodes are shared by several rows (row-per-warp kernel) and hold density / field
 // un-multiplied; the row's cp^2/f^2 and g_p/f are applied here (two more FP64 multiplies per point).
 // X and the two field terms of ah_hot at one grid point, from the staged levels.
-template <int PATH, bool ROWSCALE>
+// ABS: `nodes` is the absolute-level view (staged window - jlo), indexed by j itself.
+template <int PATH, bool ROWSCALE, bool ABS = false>
 __device__ __forceinline__ void fast_xy(double h, int j, const Node* nodes, const RowConst& rc, double* X_out,
                                         double* yth_out, double* yl_out) {
-  const Node& nd = nodes[j - rc.jlo];
+  const Node& nd = nodes[ABS ? j : j - rc.jlo];
   const double t = h - nd.alt;
   double X = fma(nd.sx, t, nd.x);
   if (ROWSCALE) X *= rc.kx;
@@ -979,11 +989,11 @@ __device__ __forceinline__ void fast_xy(double h, int j, const Node* nodes, cons
 // 0 < 1 - X < 1e-7, tested on the high word (0x3E7AD7F2 is the high word of 1e-7); see near_reflection_tail.
 __device__ __forceinline__ bool near_reflection(double X) { return (unsigned)__double2hiint(1.0 - X) < 0x3E7AD7F2u; }
 
-template <int MODE, int PATH, bool ROWSCALE>
+template <int MODE, int PATH, bool ROWSCALE, bool ABS = false>
 __device__ __forceinline__ double fast_point(double h, int j, const Node* nodes, const RowConst& rc, double* mu_out,
                                              double* q_out, bool* near_out) {
   double X, yth, yl;
-  fast_xy<PATH, ROWSCALE>(h, j, nodes, rc, &X, &yth, &yl);
+  fast_xy<PATH, ROWSCALE, ABS>(h, j, nodes, rc, &X, &yth, &yl);
   *near_out = (MODE == 0) && near_reflection(X);
   return ah_hot<MODE>(X, yth, yl, mu_out, q_out);
 }
@@ -1120,6 +1130,102 @@ __device__ __forceinline__ double tile_sum_fast(const Node* nodes, const RowCons
   return acc0 + acc1;
 }
 
+// ---- hot loop of the tile kernels, "m-space" form ----
+// The tile kernels stage their nodes for ONE row, so the row's span h_c - alt0 can be folded into the staged values:
+// a node stores m_j = (alt_j - alt0) / span and slopes per unit of m, the loop interpolates on t = m_i - m_j straight
+// from the stretched-grid multiplier, and the weights come from the table dm_i = m_{i+1} - m_i with the sum scaled by
+// span once at the end (lib:413-416: h_i = m_i span + alt0, dh_i = h_{i+1} - h_i = span dm_i up to the rounding of
+// h).  Against the altitude-space loop (tile_sum_fast, still used by the row-per-warp and the global-memory kernels,
+// whose nodes are shared between rows) this drops h_i, h_{i+1}, h_{i+2} and the two subtractions for dh from every
+// pair of points: 78 instead of 89 FP64 instructions per pair.  The tables are padded by kMultPad entries, so the
+// read one iteration ahead needs no bounds test; validity enters through one predicated DFMA (add_kept).
+template <int PATH, bool UNIFORM>
+__device__ __noinline__ double near_reflection_tail_m(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                      const double* __restrict__ dm, int first, int i1, int n_points) {
+  const double c1 = rc.span * rc.inv_dalt;
+  double acc = 0.0;
+  for (int i = first; i < i1; i += 2 * rc.group) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = i + u;
+      const double mk = __ldg(m + k);
+      const int g = __double2int_rd(mk * c1);
+      const int j = UNIFORM ? min(max(g, rc.jlo), rc.jhi) : find_bracket_pos(mk, nodes, rc.jlo, rc.jhi, g);
+      double X, yth, yl, mu, q;
+      fast_xy<PATH, false>(mk, j, nodes, rc, &X, &yth, &yl);
+      if (!near_reflection(X) || k >= i1 || k == n_points - 1) continue;   // (the last point is added by the caller)
+      const double p = ah_hot<0>(literal_x(mk, j, rc), yth, yl, &mu, &q);
+      acc = fma(keep_term(p, q) ? p : 0.0, __ldg(dm + k) * rc.span, acc);
+    }
+  }
+  return acc;
+}
+
+template <int MODE, int PATH, bool UNIFORM>
+__device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                  const double* __restrict__ dm, int i0, int i1, int n_points) {
+  double acc0 = 0.0, acc1 = 0.0;                                     // in units of the span
+  int first_near = 0x7fffffff;
+  const int il_row = n_points - 1;
+  const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
+  const double2* m2 = reinterpret_cast<const double2*>(m);           // i0 is even, both tables are 16-byte aligned
+  const double2* d2 = reinterpret_cast<const double2*>(dm);
+  int ip = (i0 >> 1) + rc.lane0;                                     // index of this thread's pair of points
+  const int ip_end = (i1 + 1) >> 1;
+  double2 mm_next = __ldg(m2 + ip), dd_next = __ldg(d2 + ip);
+  const Node* nb = nodes - rc.jlo;                                   // absolute-level view of the staged window
+#pragma unroll 2
+  for (; ip < ip_end; ip += rc.group) {                              // (unrolled by two: the read-ahead registers
+    const int i = 2 * ip;                                            //  alternate instead of being copied)
+    const double2 mm = mm_next, dd = dd_next;
+    mm_next = __ldg(m2 + ip + rc.group);                             // next iteration's entries (padded tables)
+    dd_next = __ldg(d2 + ip + rc.group);
+    int j0, j1;
+    if (UNIFORM) {
+      j0 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
+      j1 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.y * c1));
+    } else {
+      j0 = find_bracket_pos(mm.x, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
+      j1 = find_bracket_pos(mm.y, nodes, rc.jlo, rc.jhi, j0);
+    }
+    double mu0, mu1, q0, q1;
+    bool near0, near1;
+    const double p0 = fast_point<MODE, PATH, false, true>(mm.x, j0, nb, rc, &mu0, &q0, &near0);
+    const double p1 = fast_point<MODE, PATH, false, true>(mm.y, j1, nb, rc, &mu1, &q1, &near1);
+    if (MODE == 0) {
+      // the row's very last point carries weight 0 in this loop and is evaluated after it: it must not trigger the tail
+      near0 = near0 && (i != il_row);
+      near1 = near1 && (i + 1 != il_row);
+      if (near0 || near1) first_near = min(first_near, i);          // left to near_reflection_tail_m
+      if (!near0) add_kept(acc0, p0, q0, dd.x);                     // nansum (lib:288)
+      if (!near1) add_kept(acc1, p1, q1, dd.y);
+    } else {
+      add_kept(acc0, p0, q0, dd.x);
+      // (when n_points is odd the last pair's second point is a pad entry: m == 1, weight 0)
+      add_kept(acc1, p1, q1, dd.y);
+    }
+  }
+  double acc_km = 0.0;
+  if (MODE == 0 && first_near != 0x7fffffff)
+    acc_km = near_reflection_tail_m<PATH, UNIFORM>(nodes, rc, m, dm, first_near, i1, n_points);
+  // lib:416: the row's last grid point weighs 1e-6 km.  Its table weight is 0, so it went through the loop for nothing;
+  // its owner adds the term here instead of two selects per iteration.
+  const int il = n_points - 1, ipl = il & ~1;
+  if (ipl >= i0 && ipl < i1 && ((ipl - i0) >> 1) % rc.group == rc.lane0) {
+    const double ml = __ldg(m + il);
+    const int g = __double2int_rd(ml * c1);
+    const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, g) : find_bracket_pos(ml, nodes, rc.jlo, rc.jhi, g);
+    double Xl, ythl, yll, mul, ql;
+    fast_xy<PATH, false>(ml, jl, nodes, rc, &Xl, &ythl, &yll);
+    // (coarse grids: the last point is the only one this close, and with its weight of 1e-6 km an ulp of X is worth
+    //  < 1e-11 of the virtual height -- not worth an IEEE sqrt and two divisions on one lane of a 200-point row)
+    if (MODE == 0 && n_points >= 1024 && near_reflection(Xl)) Xl = literal_x(ml, jl, rc);
+    const double pl = ah_hot<MODE>(Xl, ythl, yll, &mul, &ql);
+    acc_km = fma(keep_term(pl, ql) ? pl : 0.0, kBackoff, acc_km);
+  }
+  return fma(acc0 + acc1, rc.span, acc_km);
+}
+
 // Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
 // of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
 // kernel (group = warp, ROWSCALE).
@@ -1148,6 +1254,21 @@ __device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& 
       mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
     }
   }
+  if (np >= 2 && isfinite(mup0)) {
+    // mu' is one number, so the row's sum is mu' * sum(dh_i), and the weights telescope: dh_i = h_{i+1} - h_i
+    // (lib:415) over [i0, i1) adds up to h(i1) - h(i0), plus the final 1e-6 (lib:416) in the row's last tile.  On the
+    // rows this path exists for -- reflection at/below the first level, h_c = alt0 - 1e-6 -- all h_i lie within 1e-6 km
+    // of each other, every difference is exact (Sterbenz) and so is their sum; what is left, mu' * (h_c - alt0 + 1e-6)
+    // ~ mu' * 4e-15 km, is the residue SURVEY.md 7/2 describes (the reference returns alt_min to the last bit or two).
+    // 20 % of the reflecting rows of the global grid are of this kind; they used to walk all n_points grid points.
+    // (An infinite mu' -- mu == 0 exactly -- keeps the term-by-term loop: its +inf and -inf terms make NaN.)
+    if (rc.lane0 != 0) return 0.0;
+    const bool last = (i1 >= np);
+    const double h_a = __dadd_rn(__dmul_rn(__ldg(m + i0), rc.span), rc.alt0);              // lib:413
+    const double h_b = __dadd_rn(__dmul_rn(__ldg(m + (last ? np - 1 : i1)), rc.span), rc.alt0);
+    const double term = mup0 * __dsub_rn(h_b, h_a);
+    return last ? fma(mup0, kBackoff, term) : term;
+  }
   return tile_sum<MODE, kPathFast0, true>(nodes, rc, m, i0, i1, np, mup0);
 }
 
@@ -1157,11 +1278,21 @@ __device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& 
 template <int MODE, bool LITERAL, bool ROWSCALE>
 __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& rc, int flags, int path, bool const_mup,
                                              double den0, double b0, double psi0, const double* __restrict__ m,
-                                             int i0, int i1, int np) {
+                                             const double* __restrict__ dm, int i0, int i1, int np) {
   if (const_mup) return const_mup_sum<MODE, LITERAL>(nodes, rc, path, den0, b0, psi0, m, i0, i1, np);
   if (path < kPathGeneral) {
     // uniform grids with more than one staged level take the branch-free bracket
     const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
+    if (!ROWSCALE) {                                        // nodes staged for this row alone: m-space loop
+      if (path == kPathFast0)
+        return uni ? tile_sum_fast_m<MODE, kPathFast0, true>(nodes, rc, m, dm, i0, i1, np)
+                   : tile_sum_fast_m<MODE, kPathFast0, false>(nodes, rc, m, dm, i0, i1, np);
+      if (path == kPathFastS)
+        return uni ? tile_sum_fast_m<MODE, kPathFastS, true>(nodes, rc, m, dm, i0, i1, np)
+                   : tile_sum_fast_m<MODE, kPathFastS, false>(nodes, rc, m, dm, i0, i1, np);
+      return uni ? tile_sum_fast_m<MODE, kPathFastL, true>(nodes, rc, m, dm, i0, i1, np)
+                 : tile_sum_fast_m<MODE, kPathFastL, false>(nodes, rc, m, dm, i0, i1, np);
+    }
     if (path == kPathFast0)
       return uni ? tile_sum_fast<MODE, kPathFast0, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
                  : tile_sum_fast<MODE, kPathFast0, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
@@ -1179,10 +1310,15 @@ __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& 
 // Stage profile levels [k0, k0 + n) into shared memory.  Fast paths: slopes through one fast reciprocal, density
 // and field multiplied by (kx, ky) (the row's cp^2/f^2 and g_p/f, or 1 when the nodes are shared between rows);
 // other paths: raw values and numpy's slopes.
+// m_space (fast paths of the tile kernels): the node's coordinate becomes m_j = (alt_j - alt0) / span and the slopes
+// are taken per unit of m (tile_sum_fast_m); span = 0 keeps altitude space.
 __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, int path, const ProfileRecord& rec,
                                             const double* g_alt, const double* g_den, const double* g_b,
-                                            const double* g_psi, double kx, double ky, int tid0, int nthr) {
+                                            const double* g_psi, double kx, double ky, int tid0, int nthr,
+                                            double span = 0.0) {
   const bool fast = path < kPathGeneral;
+  const bool m_space = fast && span != 0.0;
+  const double inv_span = m_space ? rcp_fast(span) : 0.0;
   for (int q = tid0; q < n; q += nthr) {
     const int k = k0 + q;
     const bool inner = k + 1 < nt;
@@ -1199,6 +1335,12 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
       nd.y = b0 * ky;
       nd.sy = ((b1 - b0) * ky) * inv_dx;
       nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
+      if (m_space) {
+        nd.alt = (a0 - rec.alt0) * inv_span;
+        nd.sx *= span;
+        nd.sy *= span;
+        nd.srad *= span;
+      }
       if (path == kPathFast0) {
         // constant field angle: interpolate YTh = Y sin(psi)/sqrt(2) and YL = Y cos(psi) directly
         const double sh = rec.sn0 * 0.70710678118654752, cc = rec.cs0;
@@ -1355,7 +1497,8 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
-  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads);
+  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads,
+              const_mup ? 0.0 : span);
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
@@ -1365,7 +1508,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   rc.kx = kx;
   rc.ky = ky;
   const double acc = row_points<MODE, LITERAL, false>(nodes, rc, rec.flags, path, const_mup, g_den[0], g_b[0], g_psi[0],
-                                                      p.mult, i0, i1, p.n_points);
+                                                      p.mult, p.dmult, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
   finish_tile(p, sc, acc, lrow, seg, n_seg, prof * p.n_freq + r, rec.alt_min);
@@ -1413,7 +1556,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
   // While the row-setup grid is still running (PDL): pull the multiplier table into L2.  It does not depend
   // on K1, and after an L2 flush its first touch would otherwise be a DRAM miss inside the grid loop.
   if (p.live_count != nullptr) {
-    const size_t bytes = sizeof(double) * (size_t)(p.n_points + kMultPad);
+    const size_t bytes = sizeof(double) * 2 * mult_table_len(p.n_points);      // [m | dm], contiguous
     for (size_t off = ((size_t)blockIdx.x * kTileThreads + threadIdx.x) * 128; off < bytes;
          off += (size_t)gridDim.x * kTileThreads * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.mult) + off));
@@ -1422,8 +1565,12 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
   if (p.live_count == nullptr) {
     const unsigned tile = blockIdx.x;                     // grid.x itself is 32-bit
     const unsigned lrow = (p.n_seg == 1) ? tile : tile / (unsigned)p.n_seg;
+    // Two rows out of three of a global batch do not reflect: their CTAs leave on the row's span before anything
+    // else is computed or loaded (the row-setup kernel already wrote their NaN).
+    const double span = p.row_span[lrow];
+    if (!(span == span)) return;
     const int seg = (p.n_seg == 1) ? 0 : (int)(tile - lrow * (unsigned)p.n_seg);
-    tile_body<MODE, LITERAL>(p, lrow, p.row_span[lrow], nullptr, seg, p.n_seg, p.seg_len, smem_raw, sc);
+    tile_body<MODE, LITERAL>(p, lrow, span, nullptr, seg, p.n_seg, p.seg_len, smem_raw, sc);
     return;
   }
   planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
@@ -1485,8 +1632,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
     const bool const_mup = (!(span > 0.0) || nt == 1) && !unsorted;   // h_c <= alt0: every point clamps to level 0
     rc.jlo = 0;
     rc.jhi = const_mup ? 0 : nt - 1;
-    double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, p.mult, 0,
-                                                 p.n_points, p.n_points);
+    double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, p.mult, p.dmult,
+                                                 0, p.n_points, p.n_points);
     acc = warp_sum(acc);
     if (lane == 0) {
       if (acc == 0.0) acc = CUDART_NAN;                   // lib:290
@@ -1547,7 +1694,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_global_
   const int i0 = seg * p.seg_len, i1 = min(p.n_points, i0 + p.seg_len);
   const Node* nodes = reinterpret_cast<const Node*>(p.node_table) + (size_t)lprof * A;
   const double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, g_den[0],
-                                                     p.bmag[prof * A], p.bpsi[prof * A], p.mult, i0, i1, p.n_points);
+                                                     p.bmag[prof * A], p.bpsi[prof * A], p.mult, p.dmult, i0, i1,
+                                                     p.n_points);
   finish_tile(p, sc, acc, lrow, seg, p.n_seg, prof * p.n_freq + r, rec.alt_min);
 }
 
@@ -1581,9 +1729,13 @@ __global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_solo_kernel(
     // the row scan
     asm volatile("" ::"d"(p.freq_scale), "l"(p.row_span), "l"(p.partial));
     const char* mseg = reinterpret_cast<const char*>(p.mult + i0);
-    const int n_lines = (int)(((size_t)(i1 - i0 + kMultPad) * sizeof(double) + 127) / 128);
+    const char* dseg = reinterpret_cast<const char*>(p.dmult + i0);
+    const int n_lines = (int)(((size_t)(i1 - i0 + 4) * sizeof(double) + 127) / 128);
     const int line = (int)(lrow % p.n_freq) + (int)threadIdx.x * p.n_freq;
-    if (line < n_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(mseg + (size_t)line * 128));
+    if (line < n_lines) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(mseg + (size_t)line * 128));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(dseg + (size_t)line * 128));
+    }
   }
   if (threadIdx.x == 0) s_span = CUDART_NAN;
   rows_body(p, MODE, lrow, reinterpret_cast<double*>(smem_raw), sc, &s_rec, &s_span);   // syncs internally
@@ -1871,10 +2023,11 @@ cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t 
   return literal ? launch_solo_t<1, true>(p, n_tiles, stream) : launch_solo_t<1, false>(p, n_tiles, stream);
 }
 
-cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream) {
+cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, cudaStream_t stream) {
   const double step = (n > 1) ? 1.0 / (double)(n - 1) : 0.0;
-  const int np = n + kMultPad;
+  const int np = (int)n_padded;
   grid_multiplier_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, step, m);
+  if (dm) grid_dmult_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, m, dm);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,11 @@ constexpr int kTileMinBlocks = PRHF_TILE_MINB;    // K2 resident CTAs per SM the
 constexpr int kSoloMinBlocks = 3;                 // the single-launch kernel carries the row setup as well: 80 registers
 constexpr int kRowsPerCta = kThreads / 32;   // K1: one warp per sounding frequency
 constexpr int kRowWarpMaxPoints = 4096;      // direct-mode calls with n_points up to this use the row-per-warp kernel
-constexpr int kMultPad = 4;                  // extra multiplier-table entries (value 1) past n_points
+// extra multiplier-table entries (value 1, weight 0) past n_points: the grid loop reads its tables one iteration
+// (2 * kTileThreads points) ahead without a bounds test
+constexpr int kMultPad = 2 * PRHF_TILE_THREADS + 4;
+// entries of the multiplier table m (even, so that the weight table dm that follows it stays 16-byte aligned)
+__host__ __device__ inline size_t mult_table_len(int n_points) { return ((size_t)n_points + kMultPad + 1) & ~(size_t)1; }
 
 constexpr int kFlagIso = 1;       // unmagnetised branch (lib:201)
 constexpr int kFlagGeneral = 2;   // non-finite node values / non-increasing altitudes / large angle steps
@@ -62,7 +66,8 @@ struct VfoParams {
   int64_t alt_stride;      // 0 = shared
   int n_alt;
   int64_t profile_offset;  // first profile handled by this launch
-  const double* mult;      // stretched-grid multiplier [n_points + kMultPad]
+  const double* mult;      // stretched-grid multiplier m [mult_table_len(n_points)]
+  const double* dmult;     // left-Riemann weights dm_i = m_{i+1} - m_i (0 from the last point on), same length
   int n_points;
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
@@ -110,7 +115,7 @@ cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t 
 size_t vfo_node_bytes();
 cudaError_t launch_vfo_nodes_global(const VfoParams& p, bool literal, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
-cudaError_t launch_grid_multiplier(int n, double* m, cudaStream_t stream);
+cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
 cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
