@@ -48,13 +48,6 @@ extern "C" {
 #define PRHF_FLAG_LITERAL 1u /* evaluate library.py:209-254 operation by operation (IEEE div/sqrt, \
                                 libdevice sincos) instead of the restructured fast form */
 
-#define PRHF_FLAG_MIXED_F32 2u /* optional mixed precision: grid points with mu^2 >= 4e-3 (about 80 % of a stretched \
-                                  row) evaluate the Appleton-Hartree block in float, the points next to the reflection \
-                                  level, every mask and every sum stay in double.  Measured bound on the virtual height: \
-                                  see DESIGN.md (about 1e-6 relative; the default path is 1e-9).  Takes effect in the tile \
-                                  kernel (n_points >= 2048, fast evaluation paths); elsewhere the flag is accepted and \
-                                  the computation is double precision */
-
 /* per-profile status values */
 #define PRHF_PROFILE_OK 0
 #define PRHF_PROFILE_NEGATIVE_DENSITY 1

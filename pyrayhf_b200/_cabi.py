@@ -17,7 +17,6 @@ ERR_CUDA = 3
 ERR_NALT_TOO_LARGE = 4
 ERR_NO_DEVICE = 5
 FLAG_LITERAL = 1
-FLAG_MIXED_F32 = 2
 
 # every symbol include/pyrayhf_b200.h declares
 EXPORTED_SYMBOLS = (

@@ -430,18 +430,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
   const int64_t rows_total = n_profiles * (int64_t)n_freq;
   const bool literal = (flags & PRHF_FLAG_LITERAL) != 0;
   const bool big = too_long_for_smem(ctx, n_alt);             // global-memory form: direct mode only
-  // optional mixed precision: takes effect in the tile kernel (batches and single profiles with n_points >= 2048 on
-  // the fast evaluation paths); every other decomposition computes in double precision whatever the flag says
-  const int mixed_cap = ((flags & PRHF_FLAG_MIXED_F32) && !literal && !big)
-                            ? prhf::vfo_mixed_cap(n_alt, ctx->max_smem_per_sm) : 0;
-  const bool mixed = mixed_cap > 0;
   CallMode cm = call_mode(ctx, rows_total, n_points, big ? 1 : n_alt);
-  if (mixed && cm.solo) {                                     // single profile: through the planned two-kernel mode
-    cm.solo = false;
-    cm.planned = true;
-    cm.ctas_per_sm = prhf::vfo_tile_ctas_per_sm(n_alt, ctx->max_smem_per_sm, false);
-    cm.slots = ctx->sm_count * cm.ctas_per_sm;
-  }
   if (big) {
     cm.solo = cm.planned = false;
     cm.ctas_per_sm = prhf::kTileMinBlocks;
@@ -571,7 +560,6 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.row_hc = nullptr;
     P.levels_in_global = big ? 1 : 0;
     P.node_table = ctx->node_table;
-    P.mixed_cap = mixed_cap;
     if (big) {
       // row setup (thread per frequency, levels read in place) -> node table -> tiles; plain stream order
       P.use_pdl = 0;
@@ -636,7 +624,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
       PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
       if (rowwarp) PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));
-      else PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream, mixed));
+      else PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
       PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
       PRHF_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
       float a = 0.f, b = 0.f;
@@ -649,7 +637,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       continue;
     }
     PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
-    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream, mixed));
+    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
     ctx->launches += 2;
   }
   return PRHF_OK;

@@ -220,66 +220,6 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
   return fma(nc, br, mu);
 }
 
-// ---- single-precision Appleton-Hartree for the optional mixed mode (PRHF_FLAG_MIXED_F32) ----
-// Same formulas as ah_hot in float: 25 FP32 operations and two MUFU.RSQ per point on the FP32 pipes instead of 33
-// operations on the (half as wide) FP64 pipe.  Only usable away from the reflection level: mu^2 = E / D is formed
-// from E = D - X (1 - X), whose relative error is eps_f32 * D / E = 6e-8 / mu^2, so the caller accepts the result
-// only where mu^2 >= kMixedMinMu2 (relative error of mu' at most ~2e-5 there, typically 1e-7 .. 1e-6) and evaluates
-// every other point -- the last ~20 % of a stretched row, where mu^2 falls to 1e-8 -- in double precision.
-// Returns mu', *u_out = mu^2, *q_out = X (1 - X) / D.
-#ifndef PRHF_MIXED_MIN_MU2
-#define PRHF_MIXED_MIN_MU2 4e-3f
-#endif
-constexpr float kMixedMinMu2 = PRHF_MIXED_MIN_MU2;
-__device__ __forceinline__ float rsqrt_f32(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <int MODE>
-__device__ __forceinline__ float ah_hot_f32(float X, float YTh, float YL, float* u_out, float* q_out) {
-  const float Xm1 = 1.0f - X;
-  const float a = YTh * YTh;
-  const float w = (YL * YL) * Xm1;
-  const float a2 = a * a;
-  const float alpha = fmaf(w, Xm1, a2);
-  const float rb = rsqrt_f32(alpha);
-  const float beta = alpha * rb;
-  const float P = a + beta;
-  const float T = fmaf(a2, rb, beta);
-  float mu, nc, q, u, dDdX, hYd;
-  if (MODE == 1) {
-    const float D = Xm1 - P;
-    const float XX = X * Xm1;
-    const float E = D - XX;
-    const float rs = rsqrt_f32(D * E);
-    const float t1 = E * rs;
-    const float inv_d = t1 * rs;
-    mu = fabsf(t1);
-    q = XX * inv_d;
-    u = E * inv_d;
-    nc = -copysignf(rs, t1);
-    dDdX = fmaf(w, rb, -1.0f);
-    hYd = fmaf(-0.5f, T, -a);
-  } else {
-    const float N = fmaf(Xm1, P, w);
-    const float G = P + w;
-    const float z = Xm1 * N;
-    const float rs = rsqrt_f32(z * (Xm1 * G));
-    const float v = z * rs;
-    mu = fabsf(v);
-    q = (X * P) * (v * (Xm1 * rs));
-    u = v * v;
-    nc = -(P * rs);
-    dDdX = -fmaf(w, rb, 1.0f);
-    hYd = fmaf(0.5f, T, -a);
-  }
-  const float br = fmaf(q, hYd, X * fmaf(q, dDdX, X - Xm1));
-  *u_out = u;
-  *q_out = q;
-  return fmaf(nc, br, mu);
-}
-
 // mu' is kept when the reference keeps it: mu not NaN (lib:233), mu <= 1 (lib:238), mu' itself not NaN
 // (nansum, lib:288).  Integer tests on the IEEE bit patterns.
 // lib:238 is decided on q = X (1-X) / D rather than on mu: the reference's mu is sqrt(fl(1 - q)), which exceeds 1

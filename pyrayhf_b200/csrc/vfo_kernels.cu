@@ -787,13 +787,6 @@ struct __align__(16) Node {
   double sn, cs;       // sin / cos of the field angle at the level (general paths: angle in degrees, unused)
 };
 
-// Single-precision copy of a fast-path node for the mixed mode (32 bytes, 2 x LDS.128); same fields as Node's
-// m-space form: Fast0 {x, sx, yth, syth, yl, syl}, FastS {x, sx, y, sy, srad, sn, cs}.
-struct __align__(16) NodeF {
-  float x, sx, y, sy;
-  float srad, sn, cs, pad;
-};
-
 struct RowConst {
   double f_hz;      // lib:491
   double alt0;      // aalt[0]
@@ -1168,36 +1161,10 @@ __device__ __noinline__ double near_reflection_tail_m(const Node* nodes, const R
   return acc;
 }
 
-// X and the two field terms at one grid point in single precision (mixed mode): t = m_i - m_j is formed in double (the
-// stretched grid's last spacings are 2e-8 of the span) and everything after it in float.
-template <int PATH>
-__device__ __forceinline__ void fast_xy_f32(double mval, int j, const Node* nb, const NodeF* nfb, float* X, float* yth,
-                                            float* yl) {
-  const float t = (float)(mval - nb[j].alt);
-  const float4 a = *reinterpret_cast<const float4*>(&nfb[j].x);
-  const float4 b = *reinterpret_cast<const float4*>(&nfb[j].srad);
-  *X = fmaf(a.y, t, a.x);
-  if (PATH == kPathFast0) {
-    *yth = fmaf(a.w, t, a.z);                       // y = Y sin(psi)/sqrt(2), sy its slope
-    *yl = fmaf(b.y, t, b.x);                        // srad = Y cos(psi), sn its slope
-    return;
-  }
-  const float Y = fmaf(a.w, t, a.z);
-  const float d = b.x * t;                          // rotation of the field angle inside the level (<= 4e-4 rad)
-  const float e2 = (-0.5f * d) * d;
-  const float sn = fmaf(b.y, e2, fmaf(d, b.z, b.y));
-  const float cs = fmaf(b.z, e2, fmaf(-d, b.y, b.z));
-  *yth = (Y * sn) * 0.70710678f;
-  *yl = Y * cs;
-}
-
-template <int MODE, int PATH, bool UNIFORM, bool MIXED = false>
+template <int MODE, int PATH, bool UNIFORM>
 __device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
-                                                  const double* __restrict__ dm, int i0, int i1, int n_points,
-                                                  const NodeF* nodes_f = nullptr) {
+                                                  const double* __restrict__ dm, int i0, int i1, int n_points) {
   double acc0 = 0.0, acc1 = 0.0;                                     // in units of the span
-  bool use64 = !MIXED || PATH == kPathFastL || nodes_f == nullptr;   // mixed mode: warp-uniform, sticky once set
-  const NodeF* nfb = MIXED ? nodes_f - rc.jlo : nullptr;
   int first_near = 0x7fffffff;
   const int il_row = n_points - 1;
   const double c1 = rc.span * rc.inv_dalt;                           // bracket guess = floor(m_i * c1)
@@ -1220,25 +1187,6 @@ __device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowCo
     } else {
       j0 = find_bracket_pos(mm.x, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
       j1 = find_bracket_pos(mm.y, nodes, rc.jlo, rc.jhi, j0);
-    }
-    if (MIXED && !use64) {
-      // single-precision attempt; accepted when every lane's two points are far enough from the reflection level
-      float X0, y0, l0, X1, y1, l1, u0, u1, qf0, qf1;
-      fast_xy_f32<PATH>(mm.x, j0, nb, nfb, &X0, &y0, &l0);
-      fast_xy_f32<PATH>(mm.y, j1, nb, nfb, &X1, &y1, &l1);
-      const float pf0 = ah_hot_f32<MODE>(X0, y0, l0, &u0, &qf0);
-      const float pf1 = ah_hot_f32<MODE>(X1, y1, l1, &u1, &qf1);
-      const bool fin0 = fabsf(pf0) < CUDART_INF_F, fin1 = fabsf(pf1) < CUDART_INF_F;
-      const bool ok = fin0 && fin1 && u0 >= kMixedMinMu2 && u1 >= kMixedMinMu2;
-      // (the lanes of a warp leave the loop at different trip counts in a tile's last iteration: vote among the
-      //  lanes that are still here)
-      if (__all_sync(__activemask(), ok)) {
-        // lib:238 on q as in keep_term: the reference drops a term when q < -3 * 2^-53 (mu > 1)
-        const float s = fmaf(qf0 > -3.3306691e-16f ? pf0 : 0.0f, (float)dd.x, (qf1 > -3.3306691e-16f ? pf1 : 0.0f) * (float)dd.y);
-        acc0 += (double)s;
-        continue;
-      }
-      use64 = true;                                                  // from here on the row is too close: double precision
     }
     double mu0, mu1, q0, q1;
     bool near0, near1;
@@ -1327,22 +1275,21 @@ __device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& 
 // Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
 // of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
 // kernel (group = warp, ROWSCALE).
-template <int MODE, bool LITERAL, bool ROWSCALE, bool MIXED = false>
+template <int MODE, bool LITERAL, bool ROWSCALE>
 __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& rc, int flags, int path, bool const_mup,
                                              double den0, double b0, double psi0, const double* __restrict__ m,
-                                             const double* __restrict__ dm, int i0, int i1, int np,
-                                             const NodeF* nodes_f = nullptr) {
+                                             const double* __restrict__ dm, int i0, int i1, int np) {
   if (const_mup) return const_mup_sum<MODE, LITERAL>(nodes, rc, path, den0, b0, psi0, m, i0, i1, np);
   if (path < kPathGeneral) {
     // uniform grids with more than one staged level take the branch-free bracket
     const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
     if (!ROWSCALE) {                                        // nodes staged for this row alone: m-space loop
       if (path == kPathFast0)
-        return uni ? tile_sum_fast_m<MODE, kPathFast0, true, MIXED>(nodes, rc, m, dm, i0, i1, np, nodes_f)
-                   : tile_sum_fast_m<MODE, kPathFast0, false, MIXED>(nodes, rc, m, dm, i0, i1, np, nodes_f);
+        return uni ? tile_sum_fast_m<MODE, kPathFast0, true>(nodes, rc, m, dm, i0, i1, np)
+                   : tile_sum_fast_m<MODE, kPathFast0, false>(nodes, rc, m, dm, i0, i1, np);
       if (path == kPathFastS)
-        return uni ? tile_sum_fast_m<MODE, kPathFastS, true, MIXED>(nodes, rc, m, dm, i0, i1, np, nodes_f)
-                   : tile_sum_fast_m<MODE, kPathFastS, false, MIXED>(nodes, rc, m, dm, i0, i1, np, nodes_f);
+        return uni ? tile_sum_fast_m<MODE, kPathFastS, true>(nodes, rc, m, dm, i0, i1, np)
+                   : tile_sum_fast_m<MODE, kPathFastS, false>(nodes, rc, m, dm, i0, i1, np);
       return uni ? tile_sum_fast_m<MODE, kPathFastL, true>(nodes, rc, m, dm, i0, i1, np)
                  : tile_sum_fast_m<MODE, kPathFastL, false>(nodes, rc, m, dm, i0, i1, np);
     }
@@ -1368,7 +1315,7 @@ __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& 
 __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, int path, const ProfileRecord& rec,
                                             const double* g_alt, const double* g_den, const double* g_b,
                                             const double* g_psi, double kx, double ky, int tid0, int nthr,
-                                            double span = 0.0, NodeF* nodes_f = nullptr) {
+                                            double span = 0.0) {
   const bool fast = path < kPathGeneral;
   const bool m_space = fast && span != 0.0;
   const double inv_span = m_space ? rcp_fast(span) : 0.0;
@@ -1417,12 +1364,6 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
       nd.x = d0; nd.sx = sd; nd.y = b0; nd.sy = sb; nd.srad = sp; nd.sn = p0; nd.cs = 0.0;
     }
     nodes[q] = nd;
-    if (nodes_f) {
-      NodeF nf;
-      nf.x = (float)nd.x; nf.sx = (float)nd.sx; nf.y = (float)nd.y; nf.sy = (float)nd.sy;
-      nf.srad = (float)nd.srad; nf.sn = (float)nd.sn; nf.cs = (float)nd.cs; nf.pad = 0.f;
-      nodes_f[q] = nf;
-    }
   }
 }
 
@@ -1473,7 +1414,7 @@ __device__ __forceinline__ void finish_tile(const VfoParams& p, BlockScratch& sc
 }
 
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
-template <int MODE, bool LITERAL, bool MIXED = false>
+template <int MODE, bool LITERAL>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
                                           const ProfileRecord* rec_src, const int seg, const int n_seg,
                                           const int seg_len, unsigned char* smem_raw, BlockScratch& sc) {
@@ -1556,12 +1497,8 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
-  // (the single-precision copies get what is left of the CTA's shared-memory share: p.mixed_cap levels; a tile whose
-  //  window is longer -- far above any real profile -- simply stays in double precision)
-  NodeF* nodes_f = (MIXED && n_stage <= p.mixed_cap && path < kPathGeneral && !const_mup)
-                       ? reinterpret_cast<NodeF*>(smem_raw + sizeof(Node) * (size_t)A) : nullptr;
   stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads,
-              const_mup ? 0.0 : span, nodes_f);
+              const_mup ? 0.0 : span);
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
@@ -1570,8 +1507,8 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   rc.group = kTileThreads;
   rc.kx = kx;
   rc.ky = ky;
-  const double acc = row_points<MODE, LITERAL, false, MIXED>(nodes, rc, rec.flags, path, const_mup, g_den[0], g_b[0],
-                                                             g_psi[0], p.mult, p.dmult, i0, i1, p.n_points, nodes_f);
+  const double acc = row_points<MODE, LITERAL, false>(nodes, rc, rec.flags, path, const_mup, g_den[0], g_b[0], g_psi[0],
+                                                      p.mult, p.dmult, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
   finish_tile(p, sc, acc, lrow, seg, n_seg, prof * p.n_freq + r, rec.alt_min);
@@ -1582,7 +1519,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 // kernel is latency-bound unless only live rows get tiles and the segment count makes the live tiles fill
 // the resident-CTA slots, so every CTA sizes the tiling from the live-row count (same arithmetic in every
 // CTA, candidates prepared by the host) and strides over live_rows * n_seg tiles.
-template <int MODE, bool LITERAL, bool MIXED = false>
+template <int MODE, bool LITERAL>
 __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char* smem_raw, BlockScratch& sc) {
   const int live = (int)__ldcg(p.live_count);
   // How many segments per live row?  Measured (profiles/sweep_nseg_batch_r01.log, 2 ... 23 profiles): the step is
@@ -1607,12 +1544,12 @@ __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char*
     // written earlier in this launch sequence (possibly in this very kernel): bypass L1
     const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
     const double span = __hiloint2double(raw.w, raw.z);
-    tile_body<MODE, LITERAL, MIXED>(p, raw.x, span, nullptr, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
+    tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, t - li * n_seg, n_seg, seg_len, smem_raw, sc);
     __syncthreads();                                      // shared memory is reused by the next tile
   }
 }
 
-template <int MODE, bool LITERAL, bool MIXED = false>
+template <int MODE, bool LITERAL>
 __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(const VfoParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockScratch sc;
@@ -1633,10 +1570,10 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
     const double span = p.row_span[lrow];
     if (!(span == span)) return;
     const int seg = (p.n_seg == 1) ? 0 : (int)(tile - lrow * (unsigned)p.n_seg);
-    tile_body<MODE, LITERAL, MIXED>(p, lrow, span, nullptr, seg, p.n_seg, p.seg_len, smem_raw, sc);
+    tile_body<MODE, LITERAL>(p, lrow, span, nullptr, seg, p.n_seg, p.seg_len, smem_raw, sc);
     return;
   }
-  planned_tiles<MODE, LITERAL, MIXED>(p, smem_raw, sc);
+  planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
 }
 
 // Row-per-warp form for small n_points (direct mode): one CTA stages the profile's levels ONCE (un-scaled)
@@ -2040,11 +1977,11 @@ int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm, bool solo_kernel) {
   return by_smem < by_regs ? (by_smem < 1 ? 1 : by_smem) : by_regs;
 }
 
-template <int MODE, bool LITERAL, bool MIXED = false>
+template <int MODE, bool LITERAL>
 static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_t stream) {
-  const size_t smem = vfo_tile_smem_bytes(p.n_alt) + (MIXED ? sizeof(NodeF) * (size_t)p.mixed_cap : 0);
-  auto kern = vfo_tile_kernel<MODE, LITERAL, MIXED>;
-  cudaError_t e = grant_dynamic_smem((const void*)kern, (MIXED ? 17 : 1) + MODE * 2 + (LITERAL ? 1 : 0), smem);
+  const size_t smem = vfo_tile_smem_bytes(p.n_alt);
+  auto kern = vfo_tile_kernel<MODE, LITERAL>;
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 1 + MODE * 2 + (LITERAL ? 1 : 0), smem);
   if (e != cudaSuccess) return e;
   if (!p.use_pdl) {
     kern<<<(unsigned)n_tiles, kTileThreads, smem, stream>>>(p);
@@ -2063,18 +2000,9 @@ static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream, bool mixed) {
-  if (mixed && !literal)
-    return mode == 0 ? launch_tiles<0, false, true>(p, n_tiles, stream) : launch_tiles<1, false, true>(p, n_tiles, stream);
+cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream) {
   if (mode == 0) return literal ? launch_tiles<0, true>(p, n_tiles, stream) : launch_tiles<0, false>(p, n_tiles, stream);
   return literal ? launch_tiles<1, true>(p, n_tiles, stream) : launch_tiles<1, false>(p, n_tiles, stream);
-}
-// Levels the single-precision node copies may take so that kTileMinBlocks CTAs still fit one SM.
-int vfo_mixed_cap(int n_alt, int max_smem_per_sm) {
-  const long long share = (long long)max_smem_per_sm / kTileMinBlocks - 1024 - (long long)sizeof(Node) * n_alt;
-  long long cap = share / (long long)sizeof(NodeF);
-  if (cap > n_alt) cap = n_alt;
-  return cap < 0 ? 0 : (int)cap;
 }
 
 template <int MODE, bool LITERAL>

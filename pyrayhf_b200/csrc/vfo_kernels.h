@@ -98,7 +98,6 @@ struct VfoParams {
   // levels straight from global memory and the tile kernel reads un-scaled nodes from this per-profile table
   int levels_in_global;
   void* node_table;        // Node[profiles_in_launch x n_alt]
-  int mixed_cap;           // mixed mode: levels of single-precision node copies a tile may stage (0: mode off)
   // Kernel parameters sit in a constant bank that is cold at every launch; each 128-byte line of this struct costs
   // its first reader a miss.  Everything the single-profile path touches stays above this comment (two lines);
   // the planner's candidate tables (256 bytes, planned mode only) come last.
@@ -110,9 +109,7 @@ struct VfoParams {
 size_t vfo_smem_bytes(int n_alt);
 int vfo_tile_ctas_per_sm(int n_alt, int max_smem_per_sm, bool solo_kernel);
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream);
-cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream,
-                             bool mixed = false);
-int vfo_mixed_cap(int n_alt, int max_smem_per_sm);
+cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
 cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 size_t vfo_node_bytes();

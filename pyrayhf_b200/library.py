@@ -30,14 +30,6 @@ def _mode_code(mode):  # noqa: E302
     raise ValueError("mode must be 'O' or 'X'")
 
 
-def _flags(literal, precision):
-    """C-ABI flags word.  ``precision='mixed'`` selects the optional single/double mixed mode (grid points away from
-    the reflection level in float, everything else in double; measured bound ~1e-6 instead of 1e-9)."""
-    if precision not in ('float64', 'mixed'):
-        raise ValueError("precision must be 'float64' or 'mixed'")
-    return (_cabi.FLAG_LITERAL if literal else 0) | (_cabi.FLAG_MIXED_F32 if precision == 'mixed' else 0)
-
-
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -65,7 +57,7 @@ def _vec(a):
 
 
 def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
-                              literal=False, precision='float64', device=-1):
+                              literal=False, device=-1):
     """Calculate virtual height from ionosonde freq and ion profile (drop-in).
 
     Parameters as the reference (library.py:463-478): ``freq`` [MHz] ndarray, ``den``
@@ -77,7 +69,6 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
 
     ``literal=True`` evaluates the Appleton-Hartree block in the reference's operation
     order (debug aid; O-mode then inherits the reference's cancellation noise).
-    ``precision='mixed'`` is the optional mixed single/double mode (see ``_flags``).
     """
     if mode == 'O':                         # library.py:391-396: exact, case-sensitive
         code = 0
@@ -96,7 +87,7 @@ def vertical_forward_operator(freq, den, bmag, bpsi, alt, mode='O', n_points=200
     st = _status_buf.get(ctx)
     if st is None:
         st = _status_buf[ctx] = np.zeros(1, dtype=np.int32)
-    flags = _flags(literal, precision)
+    flags = _cabi.FLAG_LITERAL if literal else 0
     fast = ctx.fast
     if fast is not None and n_points >= 1 and type(freq) is np.ndarray and freq.ndim == 1:
         # float64 contiguous vectors go straight to the C ABI through the buffer-protocol shim
@@ -185,7 +176,7 @@ def _check_out(out, n_prof, n_freq, want_torch, device=None):
 
 
 def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
-                                      literal=False, precision='float64', errors='raise', return_status=False,
+                                      literal=False, errors='raise', return_status=False,
                                       out=None, device=None):
     """Batched operator: ``den`` is ``[P, A]``; ``bmag`` / ``bpsi`` are ``[P, A]`` or ``[A]`` (shared by all
     profiles); ``freq`` is ``[F]`` or ``[P, F]``; ``alt`` is ``[A]`` or ``[P, A]``.  Row ``p`` of the ``[P, F]``
@@ -202,7 +193,7 @@ def vertical_forward_operator_batched(freq, den, bmag, bpsi, alt, mode='O', n_po
     """
     code = _mode_code(mode)
     n_points = _n_points_checked(n_points)
-    flags = _flags(literal, precision)
+    flags = _cabi.FLAG_LITERAL if literal else 0
     if _is_torch_tensor(den):
         import torch
         ts = [freq, den, bmag, bpsi, alt]
@@ -279,7 +270,7 @@ def _addr_of(x):
 
 
 def vertical_forward_operator_streamed(freq, den, bmag, bpsi, alt, mode='O', n_points=200, *,
-                                       literal=False, precision='float64', errors='raise', return_status=False, out=None,
+                                       literal=False, errors='raise', return_status=False, out=None,
                                        out_profile_stride=None, status_out=None, chunk_profiles=0, device=None,
                                        stream=None, synchronize=True):
     """The batched operator for LARGE batches whose arrays live on the host (ideally page-locked, see
@@ -295,7 +286,7 @@ def vertical_forward_operator_streamed(freq, den, bmag, bpsi, alt, mode='O', n_p
     """
     code = _mode_code(mode)
     n_points = _n_points_checked(n_points)
-    flags = _flags(literal, precision)
+    flags = _cabi.FLAG_LITERAL if literal else 0
     arrs = [freq, den, bmag, bpsi, alt]
     for k, v in enumerate(arrs):
         if _is_torch_tensor(v):

@@ -1,5 +1,6 @@
-"""Developer probe: the optional mixed-precision mode on one ensemble member (8 192 profiles, n = 20000): time and
-deviation from the double-precision result, per mode."""
+"""Developer probe of the mixed-precision EXPERIMENT (commit 093e345 "experiment: mixed precision mode"; the mode is
+not in the product, see profiles/mixed_f32_ab_r02.txt): one ensemble member (8 192 profiles), time and deviation from
+the double-precision result, per mode.  Runs only against a library built from that commit."""
 import os
 import sys
 
