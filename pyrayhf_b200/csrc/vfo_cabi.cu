@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #include <algorithm>
 #include <array>
@@ -116,6 +117,15 @@ int fail(prhf_ctx* ctx, cudaError_t e) {
     if (_e != cudaSuccess) return fail((ctx), _e);   \
   } while (0)
 
+// Constants of the E-space grid loop (tile_sum_fast_e): the third table and the two ratios of the geometric sequence
+// E_i = exp(10 (1 - i / (n - 1))).
+void set_stretch_constants(prhf::VfoParams& P, const double* mult, int n_points) {
+  P.etab = mult + 2 * prhf::mult_table_len(n_points);
+  const double step = (n_points > 1) ? 10.0 / (double)(n_points - 1) : 0.0;
+  P.e_ratio = std::exp(-step * (double)(2 * prhf::kTileThreads));
+  P.e_weight = -std::expm1(-step) / (std::exp(10.0) - 1.0);
+}
+
 int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const double** out) {
   std::lock_guard<std::mutex> lock(ctx->mu);
   auto it = ctx->mult.find(n_points);
@@ -124,9 +134,9 @@ int get_multiplier(prhf_ctx* ctx, int n_points, cudaStream_t stream, const doubl
     return PRHF_OK;
   }
   double* m = nullptr;
-  const size_t len = prhf::mult_table_len(n_points);          // [m | dm], dm = m + len
-  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * 2 * len));
-  cudaError_t e = prhf::launch_grid_multiplier(n_points, len, m, m + len, stream);
+  const size_t len = prhf::mult_table_len(n_points);          // [m | dm | E], dm = m + len, E = m + 2 len
+  PRHF_CUDA(ctx, cudaMalloc(&m, sizeof(double) * 3 * len));
+  cudaError_t e = prhf::launch_grid_multiplier(n_points, len, m, m + len, m + 2 * len, stream);
   ctx->launches += 2;
   if (e != cudaSuccess) {
     cudaFree(m);
@@ -407,7 +417,7 @@ int prhf_debug_trace_read(prhf_ctx* ctx, int64_t n_tiles, long long* out) {
 int prhf_grid_multiplier_f64(prhf_ctx* ctx, int n_points, double* m_out, void* cuda_stream) {
   if (!ctx || n_points < 1 || !m_out) return PRHF_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
-  PRHF_CUDA(ctx, prhf::launch_grid_multiplier(n_points, (size_t)n_points, m_out, nullptr, (cudaStream_t)cuda_stream));
+  PRHF_CUDA(ctx, prhf::launch_grid_multiplier(n_points, (size_t)n_points, m_out, nullptr, nullptr, (cudaStream_t)cuda_stream));
   ctx->launches++;
   return PRHF_OK;
 }
@@ -519,6 +529,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.profile_offset = p0;
     P.mult = mult;
     P.dmult = mult + prhf::mult_table_len(n_points);
+    set_stretch_constants(P, mult, n_points);
     P.n_points = n_points;
     P.seg_len = seg_len;
     P.n_seg = n_seg;
@@ -1161,6 +1172,7 @@ int prhf_regrid_f64(prhf_ctx* ctx, const double* f_hz, int n_freq, const double*
   P.n_alt = n_alt;
   P.mult = mult;
   P.dmult = mult + prhf::mult_table_len(n_points);
+  set_stretch_constants(P, mult, n_points);
   P.n_points = n_points;
   P.seg_len = n_points;
   P.n_seg = 1;

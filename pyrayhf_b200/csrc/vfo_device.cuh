@@ -16,6 +16,10 @@ namespace prhf {
 constexpr double kCp = 8.97866275;          // lib:61
 constexpr double kGp = 2.799249247e10;      // lib:64
 constexpr double kSharp = 10.0;             // lib:363
+// lib:314-320 with sharpness 10: m = 1 - (E - 1) / (e^10 - 1) = kStretchA - kStretchB * E, E = exp(10 (1 - u))
+constexpr double kStretchDen = 22025.465794806718;    // fl(fl(e^10) - 1), the reference's denominator
+constexpr double kStretchB = 4.5401991009687765e-05;  // fl(1 / kStretchDen)
+constexpr double kStretchA = 1.0000454019910097;      // fl(1 + kStretchB)
 constexpr double kBackoff = 1e-6;           // lib:378 (the dh argument is overwritten)
 constexpr double kYTol = 1e-12;             // lib:163
 constexpr double kDeg2Rad = 0.017453292519943295;  // fl(pi/180): np.deg2rad(x) == x * (pi/180)
@@ -93,7 +97,20 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double e = fma(-(x * y), y, 1.0);              // 1 - x y^2
-  return fma(y, e * fma(e, kThreeEighths, 0.5), y);    // y (1 + e/2 + 3 e^2 / 8)
+  // y (1 + e/2 + 3 e^2 / 8) as y + (y e)(1/2 + 3 e / 8): the two factors are independent of each other, so the result
+  // is four dependent FP64 operations behind the seed instead of five (the grid loop is a latency chain)
+  return fma(y * e, fma(e, kThreeEighths, 0.5), y);
+}
+// 1/sqrt(x) and sqrt(x) from the same seed and the same correction, both five dependent operations behind the seed
+// (sqrt(x) as x * rsqrt_fast(x) would be a sixth).  s = x y is ~sqrt(x); both are scaled by 1 + e/2 + 3 e^2/8.
+__device__ __forceinline__ double rsqrt_sqrt_fast(double x, double* sqrt_out) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double s = x * y;
+  const double e = fma(-s, y, 1.0);
+  const double c = e * fma(e, kThreeEighths, 0.5);
+  *sqrt_out = fma(s, c, s);
+  return fma(y, c, y);
 }
 
 // ---- per-row scale factors of the screen and the fast paths: X = den * kx, Y = b * ky ----
@@ -183,8 +200,8 @@ __device__ __forceinline__ double ah_hot(double X, double YTh, double YL, double
   const double w = (YL * YL) * Xm1;
   const double a2 = a * a;
   const double alpha = fma(w, Xm1, a2);
-  const double rb = rsqrt_fast(alpha);
-  const double beta = alpha * rb;
+  double beta;
+  const double rb = rsqrt_sqrt_fast(alpha, &beta);
   const double P = a + beta;
   const double T = fma(a2, rb, beta);                   // beta + a^2 / beta
   double mu, nc, q, dDdX, hYd;                          // nc = -1/(D mu), hYd = (Y dD/dY) / 2

@@ -70,16 +70,25 @@ __global__ void grid_dmult_kernel(int n, int n_padded, const double* __restrict_
   dm[i] = (i < n - 1) ? __dsub_rn(m[i + 1], m[i]) : 0.0;
 }
 
-__global__ void grid_multiplier_kernel(int n, int n_padded, double step, double* __restrict__ m) {
+// e (optional): E_i = exp(10 (1 - u_i)), the exponential inside m_i; the E-space grid loop (tile_sum_fast_e) seeds its
+// recurrence from it.  Entries past n_points are 1 (= E at the row's last point).
+__global__ void grid_multiplier_kernel(int n, int n_padded, double step, double* __restrict__ m,
+                                       double* __restrict__ e) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded) return;
-  if (i >= n) { m[i] = (n > 1) ? 1.0 : 0.0; return; }    // copies of the last entry m[n-1]
+  if (i >= n) {                                  // copies of the last entry m[n-1]
+    m[i] = (n > 1) ? 1.0 : 0.0;
+    if (e) e[i] = (n > 1) ? 1.0 : exp(kSharp);
+    return;
+  }
   double u = __dmul_rn((double)i, step);        // np.linspace: arange(n) * step ...
   if (i == n - 1 && n > 1) u = 1.0;             // ... with the endpoint forced
   const double fl = __dsub_rn(1.0, u);
   const double den = __dsub_rn(exp(kSharp), 1.0);
-  const double factor = __ddiv_rn(__dsub_rn(exp(__dmul_rn(kSharp, fl)), 1.0), den);
+  const double ex = exp(__dmul_rn(kSharp, fl));
+  const double factor = __ddiv_rn(__dsub_rn(ex, 1.0), den);
   m[i] = __dsub_rn(1.0, factor);
+  if (e) e[i] = ex;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -831,6 +840,9 @@ __device__ __forceinline__ int find_bracket(double h, const Node* nodes, int jlo
   return bracket_in<8>(h, alt, j + 1, jhi);
 }
 
+// Coordinate the fast paths stage their nodes in (stage_nodes)
+enum : int { kSpaceAlt = 0, kSpaceM = 1, kSpaceE = 2 };
+
 // Evaluation paths of the grid loop
 enum : int {
   kPathFast0 = 0,    // restructured arithmetic, field angle constant with height (no rotation)
@@ -961,10 +973,17 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
 // un-multiplied; the row's cp^2/f^2 and g_p/f are applied here (two more FP64 multiplies per point).
 // X and the two field terms of ah_hot at one grid point, from the staged levels.
 // ABS: `nodes` is the absolute-level view (staged window - jlo), indexed by j itself.
+template <int PATH, bool ROWSCALE>
+__device__ __forceinline__ void fast_xy_node(double h, const Node& nd, const RowConst& rc, double* X_out,
+                                             double* yth_out, double* yl_out);
 template <int PATH, bool ROWSCALE, bool ABS = false>
 __device__ __forceinline__ void fast_xy(double h, int j, const Node* nodes, const RowConst& rc, double* X_out,
                                         double* yth_out, double* yl_out) {
-  const Node& nd = nodes[ABS ? j : j - rc.jlo];
+  fast_xy_node<PATH, ROWSCALE>(h, nodes[ABS ? j : j - rc.jlo], rc, X_out, yth_out, yl_out);
+}
+template <int PATH, bool ROWSCALE>
+__device__ __forceinline__ void fast_xy_node(double h, const Node& nd, const RowConst& rc, double* X_out,
+                                             double* yth_out, double* yl_out) {
   const double t = h - nd.alt;
   double X = fma(nd.sx, t, nd.x);
   if (ROWSCALE) X *= rc.kx;
@@ -1018,6 +1037,16 @@ __device__ __forceinline__ double literal_x(double mval, int j, const RowConst& 
 // verification cost 10 of the loop's 187 instructions per point pair.  Grids that are merely close to uniform
 // take find_bracket_pos (guess, verify, binary search).
 __device__ __forceinline__ int bracket_uniform(int jlo, int jhi, int guess) { return min(max(guess, jlo), jhi); }
+
+// m-space form of the same bracket: floor(m * c1) with c1 = span * inv_dalt, taken from ONE round-down FMA onto
+// 1.5 * 2^52 (the integer part of the exact product lands in the low word: no F2I, no separate multiply).  The tile's
+// window [jlo, jhi] is computed with this very function from the tile's first and last multiplier, and both the
+// multiplier table and x -> floor(x * c1) are monotone, so every grid point of the tile falls inside the window by
+// construction: the loop needs no clamp.  (m <= 1 and c1 < nt - 1 -- the 1e-6 km back-off of lib:407 is nine orders
+// above the rounding of c1 -- so the index never exceeds nt - 2 + 1 either.)
+__device__ __forceinline__ int bracket_floor_m(double m, double c1) {
+  return __double2loint(__fma_rd(m, c1, 6755399441055744.0));
+}
 
 // O-mode grid points with 1 - X < 1e-7 (the last few of a 20 000-point row).  mu' ~ (1 - X)^(-1/2) there and 1 - X
 // goes down to 1e-9 at the last point, so ONE ulp of X is worth up to 1e-7 of the term and, on steep profiles, more
@@ -1149,8 +1178,8 @@ __device__ __noinline__ double near_reflection_tail_m(const Node* nodes, const R
     for (int u = 0; u < 2; ++u) {
       const int k = i + u;
       const double mk = __ldg(m + k);
-      const int g = __double2int_rd(mk * c1);
-      const int j = UNIFORM ? min(max(g, rc.jlo), rc.jhi) : find_bracket_pos(mk, nodes, rc.jlo, rc.jhi, g);
+      const int j = UNIFORM ? min(max(bracket_floor_m(mk, c1), rc.jlo), rc.jhi)
+                            : find_bracket_pos(mk, nodes, rc.jlo, rc.jhi, __double2int_rd(mk * c1));
       double X, yth, yl, mu, q;
       fast_xy<PATH, false>(mk, j, nodes, rc, &X, &yth, &yl);
       if (!near_reflection(X) || k >= i1 || k == n_points - 1) continue;   // (the last point is added by the caller)
@@ -1182,8 +1211,8 @@ __device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowCo
     dd_next = __ldg(d2 + ip + rc.group);
     int j0, j1;
     if (UNIFORM) {
-      j0 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
-      j1 = bracket_uniform(rc.jlo, rc.jhi, __double2int_rd(mm.y * c1));
+      j0 = bracket_floor_m(mm.x, c1);
+      j1 = bracket_floor_m(mm.y, c1);
     } else {
       j0 = find_bracket_pos(mm.x, nodes, rc.jlo, rc.jhi, __double2int_rd(mm.x * c1));
       j1 = find_bracket_pos(mm.y, nodes, rc.jlo, rc.jhi, j0);
@@ -1213,8 +1242,8 @@ __device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowCo
   const int il = n_points - 1, ipl = il & ~1;
   if (ipl >= i0 && ipl < i1 && ((ipl - i0) >> 1) % rc.group == rc.lane0) {
     const double ml = __ldg(m + il);
-    const int g = __double2int_rd(ml * c1);
-    const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, g) : find_bracket_pos(ml, nodes, rc.jlo, rc.jhi, g);
+    const int jl = UNIFORM ? bracket_uniform(rc.jlo, rc.jhi, bracket_floor_m(ml, c1))
+                           : find_bracket_pos(ml, nodes, rc.jlo, rc.jhi, __double2int_rd(ml * c1));
     double Xl, ythl, yll, mul, ql;
     fast_xy<PATH, false>(ml, jl, nodes, rc, &Xl, &ythl, &yll);
     // (coarse grids: the last point is the only one this close, and with its weight of 1e-6 km an ulp of X is worth
@@ -1224,6 +1253,149 @@ __device__ __forceinline__ double tile_sum_fast_m(const Node* nodes, const RowCo
     acc_km = fma(keep_term(pl, ql) ? pl : 0.0, kBackoff, acc_km);
   }
   return fma(acc0 + acc1, rc.span, acc_km);
+}
+
+// ---- hot loop of the tile kernels on uniform altitude grids, "E-space" form ----
+// The stretched grid is a geometric sequence in disguise: m_i = A - B E_i with E_i = exp(10 (1 - i/(n-1))) (lib:314-320),
+// so E_{i+s} = E_i * exp(-10 s/(n-1)) and the weight of point i is dm_i = m_{i+1} - m_i = B (1 - exp(-10/(n-1))) E_i.
+// The tile's nodes are staged in the coordinate E (stage_nodes, kSpaceE: interpolation that is linear in m is linear in
+// E), each thread seeds E for its pair of points from the table once and then advances it by ONE multiplication per
+// point and iteration, and the sum is accumulated with the weights E_i and scaled by e_weight * span at the end.  The
+// loop therefore reads NO table: the m-space loop pulled 32 bytes per thread and iteration through L2 (5 TB/s over the
+// whole GPU, every CTA walks the whole 320 KB table of a 20 000-point row) and spent a third of its warp time waiting
+// for them (profiles/ncu_r02h_*: long scoreboard 2.5 of 7.8 warps) -- at the price of one more FP64 instruction per
+// point.  Rounding: the seeds are the table's own exp values; k multiplications by the correctly rounded ratio drift
+// by <= k * 1.1e-16 relative and the thread re-seeds every kReseed iterations, so E_i, and with it h_i and dh_i, stay
+// within 1e-14 relative of the table form -- the table's dm_i = fl(m_{i+1} - m_i) itself carries 5e-9 at the top of a
+// 20 000-point row, as do the reference's own dh_i = fl(h_{i+1} - h_i).
+//
+// Bracket: x = c1 (A - B E) + 2^-36 levels, taken from ONE round-down FMA onto 1.5 * 2^14, whose ulp is 2^-38: the
+// integer part of x (x < 4096 levels) lands in bits 6..17 of the high word, i.e. (high & 0x3FFC0) is the BYTE offset
+// j * sizeof(Node) of the bracketing level -- one FMA and one AND from E to the shared-memory offset, no F2I, no
+// multiply, no clamp.  Resolution 3.6e-12 levels: a point is attributed to the neighbouring segment only within that
+// distance of a level, where the continuous interpolants differ by < 1e-13 even on the steepest profiles (a coarser
+// 2^-20 was tried first and is NOT enough: next to the reflection level mu' is singular and a point 1e-6 km off a level
+// moved one row in 10^4 by up to 4e-7, profiles/ab_r02i_espace.txt).  No clamp: x > 0 because of the 2^-36 offset (m_0 is
+// 0 to ~1e-16), x < nt - 1 + 1e-10 because c1 < nt - 1 by the 1e-6 km back-off of lib:407, level nt - 1 continues the
+// last segment's line (stage_nodes), and the window staged for the tile is computed with the same instruction on the
+// tile's first and last point, widened by one level for the drift of the recurrence.
+constexpr int kReseed = 64;
+constexpr double kBracketMagic = 24576.0;                   // 1.5 * 2^14: ulp 2^-38
+constexpr double kBracketOffset = 1.4551915228366852e-11;   // 2^-36 levels
+constexpr int kBracketMaxLevels = 4095;
+struct BracketE { double kn, km; };                         // x + magic = fma(E, kn, km)
+__device__ __forceinline__ BracketE bracket_e_constants(double c1) {
+  BracketE b;
+  b.kn = -(c1 * kStretchB);
+  b.km = fma(c1, kStretchA, kBracketOffset) + kBracketMagic;
+  return b;
+}
+// byte offset of the bracketing level: j * 64
+__device__ __forceinline__ unsigned bracket_bytes_e(double E, const BracketE& b) {
+  static_assert(sizeof(Node) == 64, "bracket_bytes_e yields j * 64");
+  return (unsigned)__double2hiint(__fma_rd(E, b.kn, b.km)) & 0x3FFC0u;
+}
+__device__ __forceinline__ int bracket_floor_e(double E, const BracketE& b) { return (int)(bracket_bytes_e(E, b) >> 6); }
+
+// O-mode grid points with 1 - X < 1e-7 that the E-space loop left out (see near_reflection_tail): same thread, same
+// pairs and -- so that the "near" decision falls exactly as it fell in the loop -- the same E_i: the recurrence is
+// replayed from the seed of the re-seed block that holds the first such pair (ip_first).
+template <int PATH>
+__device__ __noinline__ double near_reflection_tail_e(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                      const double* __restrict__ dm, const double* __restrict__ etab,
+                                                      double e_ratio, int ip, int ip_first, int ip_end) {
+  const BracketE br = bracket_e_constants(rc.span * rc.inv_dalt);
+  const double2* e2 = reinterpret_cast<const double2*>(etab);
+  const Node* nb = nodes - rc.jlo;
+  double acc = 0.0;
+  while (ip + kReseed * rc.group <= ip_first) ip += kReseed * rc.group;   // whole re-seed blocks before the first pair
+  while (ip < ip_end) {
+    const double2 seed = __ldg(e2 + ip);
+    double E[2] = {seed.x, seed.y};
+    const int ip_blk = min(ip_end, ip + kReseed * rc.group);
+    for (; ip < ip_blk; ip += rc.group) {
+      if (ip >= ip_first) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = 2 * ip + u;
+          const int j = bracket_floor_e(E[u], br);
+          double X, yth, yl, mu, q;
+          fast_xy<PATH, false, true>(E[u], j, nb, rc, &X, &yth, &yl);
+          if (!near_reflection(X)) continue;
+          const double p = ah_hot<0>(literal_x(__ldg(m + k), j, rc), yth, yl, &mu, &q);
+          acc = fma(keep_term(p, q) ? p : 0.0, __ldg(dm + k) * rc.span, acc);
+        }
+      }
+      E[0] *= e_ratio;
+      E[1] *= e_ratio;
+    }
+  }
+  return acc;
+}
+
+template <int MODE, int PATH>
+__device__ __forceinline__ double tile_sum_fast_e(const Node* nodes, const RowConst& rc, const double* __restrict__ m,
+                                                  const double* __restrict__ dm, const double* __restrict__ etab,
+                                                  double e_ratio, double e_weight, int i0, int i1, int n_points) {
+  double acc0 = 0.0, acc1 = 0.0;                                     // sum of mu' E_i
+  int first_near = 0x7fffffff;
+  const int il = n_points - 1;
+  const int i_end = min(i1, il);                                     // the row's last point is added after the loop
+  const BracketE br = bracket_e_constants(rc.span * rc.inv_dalt);
+  const double2* e2 = reinterpret_cast<const double2*>(etab);        // i0 is even, the table is 16-byte aligned
+  const int ip_start = (i0 >> 1) + rc.lane0;                         // index of this thread's first pair of points
+  int ip = ip_start;
+  const int ip_end = i_end >> 1;                                     // pairs whose two points both precede i_end
+  const char* nb_bytes = reinterpret_cast<const char*>(nodes - rc.jlo);   // absolute-level view of the staged window
+  while (ip < ip_end) {
+    const double2 seed = __ldg(e2 + ip);
+    double E0 = seed.x, E1 = seed.y;
+    const int ip_blk = min(ip_end, ip + kReseed * rc.group);
+#pragma unroll 2
+    for (; ip < ip_blk; ip += rc.group) {
+      const Node& n0 = *reinterpret_cast<const Node*>(nb_bytes + bracket_bytes_e(E0, br));
+      const Node& n1 = *reinterpret_cast<const Node*>(nb_bytes + bracket_bytes_e(E1, br));
+      double X0, X1, yth0, yth1, yl0, yl1, mu0, mu1, q0, q1;
+      fast_xy_node<PATH, false>(E0, n0, rc, &X0, &yth0, &yl0);
+      fast_xy_node<PATH, false>(E1, n1, rc, &X1, &yth1, &yl1);
+      const bool near0 = (MODE == 0) && near_reflection(X0), near1 = (MODE == 0) && near_reflection(X1);
+      const double p0 = ah_hot<MODE>(X0, yth0, yl0, &mu0, &q0);
+      const double p1 = ah_hot<MODE>(X1, yth1, yl1, &mu1, &q1);
+      if (MODE == 0) {
+        if (near0 || near1) first_near = min(first_near, ip);       // left to near_reflection_tail_e
+        if (!near0) add_kept(acc0, p0, q0, E0);                     // nansum (lib:288)
+        if (!near1) add_kept(acc1, p1, q1, E1);
+      } else {
+        add_kept(acc0, p0, q0, E0);
+        add_kept(acc1, p1, q1, E1);
+      }
+      E0 *= e_ratio;
+      E1 *= e_ratio;
+    }
+  }
+  double acc_km = 0.0;
+  if (MODE == 0 && first_near != 0x7fffffff)
+    acc_km = near_reflection_tail_e<PATH>(nodes, rc, m, dm, etab, e_ratio, ip_start, first_near, ip_end);
+  // The pair that holds the row's last point (lib:416: it weighs 1e-6 km) and, when n_points is even, the point before
+  // it (a regular point the loop above left out with its pair): their owner adds them from the tables.
+  const int ipl = il >> 1;
+  if (2 * ipl >= i0 && 2 * ipl < i1 && (ipl - (i0 >> 1)) % rc.group == rc.lane0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = 2 * ipl + u;
+      if (k > il) continue;
+      const double Ek = __ldg(etab + k);
+      const int jk = min(max(bracket_floor_e(Ek, br), rc.jlo), rc.jhi);
+      double Xk, ythk, ylk, muk, qk;
+      fast_xy<PATH, false>(Ek, jk, nodes, rc, &Xk, &ythk, &ylk);
+      // (coarse grids: the last point is the only one this close, and with its weight of 1e-6 km an ulp of X is worth
+      //  < 1e-11 of the virtual height -- not worth an IEEE sqrt and two divisions on one lane of a 200-point row)
+      if (MODE == 0 && (k < il || n_points >= 1024) && near_reflection(Xk)) Xk = literal_x(__ldg(m + k), jk, rc);
+      const double pk = ah_hot<MODE>(Xk, ythk, ylk, &muk, &qk);
+      acc_km = fma(keep_term(pk, qk) ? pk : 0.0, (k == il) ? kBackoff : __ldg(dm + k) * rc.span, acc_km);
+    }
+  }
+  return fma(acc0 + acc1, e_weight * rc.span, acc_km);
 }
 
 // Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
@@ -1275,15 +1447,28 @@ __device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& 
 // Grid points [i0, i1) of one row on the evaluation path chosen for its profile; returns this thread's share
 // of the nansum.  Shared by the tile kernel (group = CTA, nodes pre-scaled for the row) and the row-per-warp
 // kernel (group = warp, ROWSCALE).
+struct StretchTables {                                      // p.mult, p.dmult, p.etab and the two ratios
+  const double *m, *dm, *e;
+  double e_ratio, e_weight;
+};
 template <int MODE, bool LITERAL, bool ROWSCALE>
 __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& rc, int flags, int path, bool const_mup,
-                                             double den0, double b0, double psi0, const double* __restrict__ m,
-                                             const double* __restrict__ dm, int i0, int i1, int np) {
+                                             double den0, double b0, double psi0, const StretchTables& st, int space,
+                                             int i0, int i1, int np) {
+  const double* __restrict__ m = st.m;
+  const double* __restrict__ dm = st.dm;
   if (const_mup) return const_mup_sum<MODE, LITERAL>(nodes, rc, path, den0, b0, psi0, m, i0, i1, np);
   if (path < kPathGeneral) {
-    // uniform grids with more than one staged level take the branch-free bracket
-    const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
-    if (!ROWSCALE) {                                        // nodes staged for this row alone: m-space loop
+    if (!ROWSCALE) {                                        // nodes staged for this row alone
+      if (space == kSpaceE) {                               // uniform altitude grid: E-space loop, no table reads
+        if (path == kPathFast0)
+          return tile_sum_fast_e<MODE, kPathFast0>(nodes, rc, m, dm, st.e, st.e_ratio, st.e_weight, i0, i1, np);
+        if (path == kPathFastS)
+          return tile_sum_fast_e<MODE, kPathFastS>(nodes, rc, m, dm, st.e, st.e_ratio, st.e_weight, i0, i1, np);
+        return tile_sum_fast_e<MODE, kPathFastL>(nodes, rc, m, dm, st.e, st.e_ratio, st.e_weight, i0, i1, np);
+      }
+      // m-space loop; uniform grids with more than one staged level take the branch-free bracket
+      const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
       if (path == kPathFast0)
         return uni ? tile_sum_fast_m<MODE, kPathFast0, true>(nodes, rc, m, dm, i0, i1, np)
                    : tile_sum_fast_m<MODE, kPathFast0, false>(nodes, rc, m, dm, i0, i1, np);
@@ -1293,6 +1478,7 @@ __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& 
       return uni ? tile_sum_fast_m<MODE, kPathFastL, true>(nodes, rc, m, dm, i0, i1, np)
                  : tile_sum_fast_m<MODE, kPathFastL, false>(nodes, rc, m, dm, i0, i1, np);
     }
+    const bool uni = (flags & kFlagUniformAlt) != 0 && rc.jhi > rc.jlo;
     if (path == kPathFast0)
       return uni ? tile_sum_fast<MODE, kPathFast0, true, ROWSCALE>(nodes, rc, m, i0, i1, np)
                  : tile_sum_fast<MODE, kPathFast0, false, ROWSCALE>(nodes, rc, m, i0, i1, np);
@@ -1312,34 +1498,46 @@ __device__ __forceinline__ double row_points(const Node* nodes, const RowConst& 
 // other paths: raw values and numpy's slopes.
 // m_space (fast paths of the tile kernels): the node's coordinate becomes m_j = (alt_j - alt0) / span and the slopes
 // are taken per unit of m (tile_sum_fast_m); span = 0 keeps altitude space.
+// `space` (fast paths of the tile kernels, whose nodes are staged for ONE row): kSpaceM -- the node's coordinate becomes
+// m_j = (alt_j - alt0) / span and the slopes are taken per unit of m (tile_sum_fast_m); kSpaceE -- the coordinate becomes
+// E_j = (A - m_j) / B, the exponential of the stretched grid at the level, slopes per unit of E (tile_sum_fast_e);
+// kSpaceAlt keeps altitude.
 __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, int path, const ProfileRecord& rec,
                                             const double* g_alt, const double* g_den, const double* g_b,
                                             const double* g_psi, double kx, double ky, int tid0, int nthr,
-                                            double span = 0.0) {
+                                            double span = 0.0, int space = kSpaceAlt) {
   const bool fast = path < kPathGeneral;
-  const bool m_space = fast && span != 0.0;
-  const double inv_span = m_space ? rcp_fast(span) : 0.0;
+  if (!fast) space = kSpaceAlt;
+  const double inv_span = (space != kSpaceAlt) ? rcp_fast(span) : 0.0;
   for (int q = tid0; q < n; q += nthr) {
     const int k = k0 + q;
     const bool inner = k + 1 < nt;
-    const double a0 = g_alt[k], d0 = g_den[k], b0 = g_b[k], p0 = g_psi[k];
-    const double a1 = inner ? g_alt[k + 1] : a0, d1 = inner ? g_den[k + 1] : d0;
-    const double b1 = inner ? g_b[k + 1] : b0, p1 = inner ? g_psi[k + 1] : p0;
+    // E space: the level at the peak-side end of the profile continues the last segment's line instead of clamping
+    // (the unclamped bracket of tile_sum_fast_e may land on it for a point within ~1e-6 levels below it)
+    const int kb = (space == kSpaceE && !inner && k > 0) ? k - 1 : k;
+    const bool seg = inner || kb != k;
+    const double a0 = g_alt[kb], d0 = g_den[kb], b0 = g_b[kb], p0 = g_psi[kb];
+    const double a1 = seg ? g_alt[kb + 1] : a0, d1 = seg ? g_den[kb + 1] : d0;
+    const double b1 = seg ? g_b[kb + 1] : b0, p1 = seg ? g_psi[kb + 1] : p0;
     Node nd;
     nd.alt = a0;
     if (fast) {
       // slopes through one fast reciprocal (<= 2 ulp from numpy's quotient; the literal paths divide)
-      const double inv_dx = inner ? rcp_fast(a1 - a0) : 0.0;
-      nd.x = d0 * kx;
+      const double inv_dx = seg ? rcp_fast(a1 - a0) : 0.0;
+      const bool ext = kb != k;                           // values of level k, slopes of the segment below it
+      nd.alt = ext ? a1 : a0;
+      nd.x = (ext ? d1 : d0) * kx;
       nd.sx = ((d1 - d0) * kx) * inv_dx;
-      nd.y = b0 * ky;
+      nd.y = (ext ? b1 : b0) * ky;
       nd.sy = ((b1 - b0) * ky) * inv_dx;
       nd.srad = ((p1 - p0) * kDeg2Rad) * inv_dx;
-      if (m_space) {
-        nd.alt = (a0 - rec.alt0) * inv_span;
-        nd.sx *= span;
-        nd.sy *= span;
-        nd.srad *= span;
+      if (space != kSpaceAlt) {
+        const double mj = (nd.alt - rec.alt0) * inv_span;
+        const double ds = (space == kSpaceE) ? -(span * kStretchB) : span;     // d alt / d coordinate
+        nd.alt = (space == kSpaceE) ? (kStretchA - mj) * kStretchDen : mj;
+        nd.sx *= ds;
+        nd.sy *= ds;
+        nd.srad *= ds;
       }
       if (path == kPathFast0) {
         // constant field angle: interpolate YTh = Y sin(psi)/sqrt(2) and YL = Y cos(psi) directly
@@ -1351,7 +1549,7 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
         nd.sn = sy0 * cc;
         nd.cs = 0.0;
       } else {
-        sincos(p0 * kDeg2Rad, &nd.sn, &nd.cs);
+        sincos((ext ? p1 : p0) * kDeg2Rad, &nd.sn, &nd.cs);
       }
     } else {
       double sd = 0.0, sb = 0.0, sp = 0.0;
@@ -1413,11 +1611,19 @@ __device__ __forceinline__ void finish_tile(const VfoParams& p, BlockScratch& sc
   p.vh[out_idx] = total + alt_min;                        // lib:292
 }
 
+// Where a tile takes its profile levels and its frequency from when they are NOT the caller's global buffers: the
+// single-launch kernel keeps the profile it staged in shared memory (and may have received it as kernel parameters).
+struct TileSrc {
+  const double *alt, *den, *b, *psi;
+  double f_mhz;
+};
+
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
                                           const ProfileRecord* rec_src, const int seg, const int n_seg,
-                                          const int seg_len, unsigned char* smem_raw, BlockScratch& sc) {
+                                          const int seg_len, unsigned char* smem_raw, BlockScratch& sc,
+                                          const TileSrc* src = nullptr) {
   const int tid = threadIdx.x;
 #ifdef PRHF_TRACE
   if (p.trace && tid == 0) {
@@ -1436,18 +1642,19 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int i1 = min(p.n_points, i0 + seg_len);
   // every load of the prologue is independent of the others: issue them together
   const ProfileRecord rec = rec_src ? *rec_src : load_profile_record(p.prof_rec + lprof);
-  const double f_mhz = p.freq[prof * p.freq_stride + r];
+  const double f_mhz = src ? src->f_mhz : p.freq[prof * p.freq_stride + r];
   const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
+  const double e_lo = __ldg(p.etab + i0), e_hi = __ldg(p.etab + i1 - 1);
   if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
   PRHF_TRACE_MARK(3);
   const int nt = rec.nt;
 
   const int path = select_path<LITERAL>(rec.flags);
   const int A = p.n_alt;
-  const double* g_den = p.den + prof * A;
-  const double* g_b = p.bmag + prof * A;
-  const double* g_psi = p.bpsi + prof * A;
-  const double* g_alt = p.alt + prof * p.alt_stride;
+  const double* g_den = src ? src->den : p.den + prof * A;
+  const double* g_b = src ? src->b : p.bmag + prof * A;
+  const double* g_psi = src ? src->psi : p.bpsi + prof * A;
+  const double* g_alt = src ? src->alt : p.alt + prof * p.alt_stride;
 
   RowConst rc;
   rc.g_alt = g_alt;
@@ -1465,6 +1672,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   PRHF_TRACE_X(10);
 
   // ---- node window of this tile: brackets of its first and last grid point ----
+  int space = kSpaceM;                                    // coordinate the fast paths stage their nodes in
   if (const_mup) {
     rc.jlo = rc.jhi = 0;
   } else if (unsorted) {
@@ -1476,9 +1684,23 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
     const int g_lo = min(max(__double2int_rd((h_lo - rc.alt0) * rec.inv_dalt), 0), nt - 1);
     const int g_hi = min(max(__double2int_rd((h_hi - rc.alt0) * rec.inv_dalt), 0), nt - 1);
     if (rec.flags & kFlagUniformAlt) {
-      // levels sit within a quarter step of the uniform grid: the guess is the bracket to +-1
-      rc.jlo = max(g_lo - 1, 0);
-      rc.jhi = min(g_hi + 1, nt - 1);
+      // levels sit within a quarter step of the uniform grid: the guess is the bracket to +-1.  The m-space loop takes
+      // floor(m_i * c1) unclamped (bracket_floor_m), so the window must contain that value for the tile's first and last
+      // multiplier -- computed here with the same instruction -- and, by monotonicity, for every point in between.
+      const double c1 = span * rec.inv_dalt;
+      const int f_lo = bracket_floor_m(m_lo, c1), f_hi = bracket_floor_m(m_hi, c1);
+      rc.jlo = max(min(g_lo - 1, f_lo), 0);
+      rc.jhi = min(max(g_hi + 1, f_hi), nt - 1);
+#ifndef PRHF_NO_ESPACE                                    // (developer A/B switch: keep the table-reading m-space loop)
+      if (path < kPathGeneral && nt <= kBracketMaxLevels && rc.jhi > rc.jlo) {
+        // E-space loop (tile_sum_fast_e): its bracket, evaluated at the tile's first and last point, +-1 level for the
+        // drift of the recurrence against the table (1e-14 relative)
+        space = kSpaceE;
+        const BracketE br = bracket_e_constants(c1);
+        rc.jlo = max(min(rc.jlo, bracket_floor_e(e_lo, br) - 1), 0);
+        rc.jhi = min(max(rc.jhi, bracket_floor_e(e_hi, br) + 1), nt - 1);
+      }
+#endif
     } else {
       if (tid == 0 || tid == 32) {                        // kTileThreads >= 64
         const double h = (tid == 0) ? h_lo : h_hi;
@@ -1497,8 +1719,8 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int n_stage = min(rc.jhi + 1, nt - 1) - rc.jlo + 1;          // levels jlo .. min(jhi+1, nt-1)
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
-  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads,
-              const_mup ? 0.0 : span);
+  if (const_mup) space = kSpaceAlt;
+  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads, span, space);
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
@@ -1507,8 +1729,9 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   rc.group = kTileThreads;
   rc.kx = kx;
   rc.ky = ky;
+  const StretchTables st{p.mult, p.dmult, p.etab, p.e_ratio, p.e_weight};
   const double acc = row_points<MODE, LITERAL, false>(nodes, rc, rec.flags, path, const_mup, g_den[0], g_b[0], g_psi[0],
-                                                      p.mult, p.dmult, i0, i1, p.n_points);
+                                                      st, space, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
   finish_tile(p, sc, acc, lrow, seg, n_seg, prof * p.n_freq + r, rec.alt_min);
@@ -1632,7 +1855,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_rowwarp_kern
     const bool const_mup = (!(span > 0.0) || nt == 1) && !unsorted;   // h_c <= alt0: every point clamps to level 0
     rc.jlo = 0;
     rc.jhi = const_mup ? 0 : nt - 1;
-    double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, p.mult, p.dmult,
+    const StretchTables st{p.mult, p.dmult, p.etab, p.e_ratio, p.e_weight};
+    double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, den0, b0, psi0, st, kSpaceAlt,
                                                  0, p.n_points, p.n_points);
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -1693,8 +1917,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_global_
   rc.jhi = const_mup ? 0 : nt - 1;
   const int i0 = seg * p.seg_len, i1 = min(p.n_points, i0 + p.seg_len);
   const Node* nodes = reinterpret_cast<const Node*>(p.node_table) + (size_t)lprof * A;
+  const StretchTables st{p.mult, p.dmult, p.etab, p.e_ratio, p.e_weight};
   const double acc = row_points<MODE, LITERAL, true>(nodes, rc, rec.flags, path, const_mup, g_den[0],
-                                                     p.bmag[prof * A], p.bpsi[prof * A], p.mult, p.dmult, i0, i1,
+                                                     p.bmag[prof * A], p.bpsi[prof * A], st, kSpaceAlt, i0, i1,
                                                      p.n_points);
   finish_tile(p, sc, acc, lrow, seg, p.n_seg, prof * p.n_freq + r, rec.alt_min);
 }
@@ -2023,10 +2248,10 @@ cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t 
   return literal ? launch_solo_t<1, true>(p, n_tiles, stream) : launch_solo_t<1, false>(p, n_tiles, stream);
 }
 
-cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, cudaStream_t stream) {
+cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, double* e, cudaStream_t stream) {
   const double step = (n > 1) ? 1.0 / (double)(n - 1) : 0.0;
   const int np = (int)n_padded;
-  grid_multiplier_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, step, m);
+  grid_multiplier_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, step, m, e);
   if (dm) grid_dmult_kernel<<<(np + 255) / 256, 256, 0, stream>>>(n, np, m, dm);
   return cudaGetLastError();
 }

@@ -68,6 +68,9 @@ struct VfoParams {
   int64_t profile_offset;  // first profile handled by this launch
   const double* mult;      // stretched-grid multiplier m [mult_table_len(n_points)]
   const double* dmult;     // left-Riemann weights dm_i = m_{i+1} - m_i (0 from the last point on), same length
+  const double* etab;      // E_i = exp(10 (1 - u_i)) (m_i = A - B E_i), same length: seeds of the E-space grid loop
+  double e_ratio;          // exp(-10 * 2 kTileThreads / (n_points - 1)): E_{i + 2 kTileThreads} / E_i
+  double e_weight;         // B (1 - exp(-10 / (n_points - 1))): dm_i = e_weight * E_i
   int n_points;
   int seg_len;             // grid points per tile (even)
   int n_seg;               // tiles per (profile, frequency) row
@@ -115,7 +118,7 @@ cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t 
 size_t vfo_node_bytes();
 cudaError_t launch_vfo_nodes_global(const VfoParams& p, bool literal, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
-cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, cudaStream_t stream);
+cudaError_t launch_grid_multiplier(int n, size_t n_padded, double* m, double* dm, double* e, cudaStream_t stream);
 cudaError_t launch_mu_mup(const double* X, const double* Y, const double* psi, int64_t n, int mode, bool iso,
                           bool literal, double* mu, double* mup, cudaStream_t stream);
 cudaError_t launch_residual(const double* vh, const double* vh_obs, int64_t n_profiles, int n_freq, double* residual,
