@@ -62,6 +62,8 @@ struct prhf_ctx {
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
   int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
+  int queue_mode = 2;                // PRHF_QUEUE: 0 large batches with one tile-kernel CTA per row (no live-row queue),
+                                     // 1 queue + static stride (slower: measurement only), 2 queue + tickets
   prhf::LiveRow* live_list = nullptr;
   size_t live_list_cap = 0;
   void* node_table = nullptr;        // un-scaled nodes of profiles too long for shared memory (n_alt > prhf_max_n_alt)
@@ -328,6 +330,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_NO_SOLO")) ctx->use_solo = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_K1_LANES")) ctx->use_k1_lanes = (atoi(s) == 0);
+  if (const char* s = getenv("PRHF_QUEUE")) ctx->queue_mode = atoi(s);
   if (const char* s = getenv("PRHF_PLAN_NSEG")) ctx->force_nseg = atoi(s);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
@@ -498,7 +501,19 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     rc = ensure_workspace(ctx, (size_t)rows_launch * n_seg, (size_t)rows_launch);
     if (rc != PRHF_OK) return rc;
   }
-  if (planned) {
+  // Queued mode (large batches through the tile kernel): the row setup, one thread per frequency, finishes the rows
+  // clamped to the first level itself and appends the rows that still need their grid points to a queue; the tile
+  // kernel runs one CTA per resident slot and strides over the queue.  Against one CTA per row this drops the launch of
+  // a CTA for every row that does not reflect (two of three on a global grid) and keeps every queued row equally long.
+  const bool lane_k1 = !planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count;
+  const bool queued = !solo && !planned && !big && lane_k1 && ctx->queue_mode > 0 &&
+                      !(n_seg == 1 && n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp);
+  if (queued) {
+    n_cand = 1;
+    cand_seg[0] = n_seg;
+    cand_len[0] = seg_len;
+  }
+  if (planned || queued) {
     rc = ensure_plan(ctx, (size_t)rows_launch);
     if (rc != PRHF_OK) return rc;
   }
@@ -535,7 +550,9 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.n_seg = n_seg;
     P.rows_per_warp = solo ? 1 : rows_per_warp;
     P.k1_solo = solo ? 1 : 0;
-    P.k1_lane_mode = (!planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count) ? 1 : 0;
+    P.k1_lane_mode = lane_k1 ? 1 : 0;
+    P.k1_finish_clamped = queued ? (literal ? 2 : 1) : 0;
+    P.queue_tickets = (queued && ctx->queue_mode >= 2) ? 1 : 0;
     P.vh = vh_out;
     P.status = status;
     P.prof_rec = ctx->prof_rec;
@@ -543,10 +560,10 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.partial = ctx->partial;
     P.counter = ctx->counter;
     P.trace = ctx->trace;
-    if (planned) {
+    if (planned || queued) {
       // the live-row counter starts every launch at zero (a 4-byte memset node: simpler and safer than any
       // hand-over of the reset between consecutive calls)
-      PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, sizeof(unsigned), stream));
+      PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, 2 * sizeof(unsigned), stream));   // [live rows, tickets]
       P.live_count = ctx->live_count;
       P.live_list = ctx->live_list;
     } else {
@@ -621,7 +638,9 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       P.rw_rows_per_cta = n_freq;
     }
     // planned mode: enough CTAs for two waves of slots; they stride over however many tiles K1 planned
-    const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots) : np * tiles_per_profile;
+    const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots)
+                       : queued  ? std::min<int64_t>(np * tiles_per_profile, (int64_t)slots)
+                                 : np * tiles_per_profile;
     if (rowwarp && !ctx->kernel_timing) {
       PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
       PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));

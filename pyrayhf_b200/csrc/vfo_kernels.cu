@@ -355,6 +355,48 @@ __device__ __noinline__ double dead_row_single_level(int mode, bool iso, double 
   return (term == term && term != 0.0) ? term + alt_min : CUDART_NAN;
 }
 
+// Rows that reflect at or below the first level (h_c <= alt0, e.g. every X-mode row below the gyrofrequency): np.interp
+// clamps every grid point to level 0, so mu' is ONE number and the row's nansum is mu' * sum(dh_i) (lib:288).
+// mu' at level 0 on the evaluation path the tile kernels would take (const_mup_sum).
+__device__ __noinline__ double level0_mup(int mode, bool iso, bool literal, double den0, double b0, double psi0,
+                                          double f_hz) {
+  const double X = x_literal(den0, f_hz);
+  if (iso) return iso_mup(X, nullptr);
+  const double Y = y_literal(b0, f_hz);
+  if (literal) return (mode == 0) ? ah_literal<0>(X, Y, psi0, nullptr) : ah_literal<1>(X, Y, psi0, nullptr);
+  double sn, cs;
+  sincos(__dmul_rn(psi0, kDeg2Rad), &sn, &cs);
+  return (mode == 0) ? ah_fast<0>(X, Y, sn, cs, nullptr) : ah_fast<1>(X, Y, sn, cs, nullptr);
+}
+// The whole row in closed form (n_points >= 2, mu' finite or NaN): the weights telescope, sum(dh_i) = h_{n-1} - h_0 +
+// 1e-6 (lib:415-416) with h_0 = alt0 (m_0 = 0) and h_{n-1} = span + alt0 (m_{n-1} = 1); a NaN mu' makes every term NaN,
+// nansum drops them all and the empty sum becomes NaN (lib:290).
+__device__ __forceinline__ double clamped_row_vh(double mup0, double span, double alt0, double alt_min) {
+  if (mup0 != mup0) return CUDART_NAN;
+  const double h_b = __dadd_rn(span, alt0);                         // lib:413 at m = 1
+  const double total = fma(mup0, kBackoff, mup0 * __dsub_rn(h_b, alt0));
+  return (total == 0.0) ? CUDART_NAN : total + alt_min;             // lib:290, lib:292
+}
+
+// Queue of the rows the tile kernel still has to do: one atomic per warp, entries of the warp's rows adjacent.
+__device__ __forceinline__ void append_live_rows(const VfoParams& p, bool live, int64_t lrow, double span) {
+  const unsigned mask = __activemask();
+  const unsigned votes = __ballot_sync(mask, live);
+  if (votes == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(votes) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(p.live_count, (unsigned)__popc(votes));
+  base = __shfl_sync(mask, base, leader);
+  if (live) {
+    LiveRow e;
+    e.row = (int)lrow;
+    e.pad = 0;
+    e.span = span;
+    p.live_list[base + __popc(votes & ((1u << lane) - 1u))] = e;
+  }
+}
+
 // `item` = (profile index inside the launch) * chunks + chunk of sounding frequencies.
 // Solo mode (p.k1_solo): the CTA belongs to ONE row (item = row index inside the launch); warp 0 scans it and
 // the outcome is also left in shared memory (*s_rec, *s_span) for the tile code that follows in the same CTA.
@@ -525,6 +567,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       if (p.row_hc) p.row_hc[lrow] = CUDART_NAN;
       return;
     }
+    // (queued mode appends with a vote among the threads that reach the append together: __activemask)
     const double f_hz = __dmul_rn(p.freq[prof * p.freq_stride + r], p.freq_scale);   // lib:491
     double kx, ky;
     row_scales(f_hz, &kx, &ky);
@@ -606,8 +649,21 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
         hcrit = __dadd_rn(__dmul_rn(slope, __dsub_rn(1.0, M)), s_alt[j]);
       }
     }
-    p.row_span[lrow] = __dsub_rn(__dsub_rn(hcrit, kBackoff), s_alt[0]);   // lib:407, lib:413
+    double span = __dsub_rn(__dsub_rn(hcrit, kBackoff), s_alt[0]);        // lib:407, lib:413
     if (p.row_hc) p.row_hc[lrow] = __dsub_rn(hcrit, kBackoff);
+    // Queued mode: rows clamped to the first level are finished here in closed form (a fifth of the reflecting rows of a
+    // global grid; in the tile kernel each would hold a CTA slot for its prologue), so that every queued row costs the
+    // same n_points grid points and the tile kernel's static stride over the queue stays balanced.  (An infinite mu' --
+    // mu == 0 exactly at level 0 -- keeps the term-by-term loop of the tile kernel: inf and -inf terms make NaN.)
+    if (p.live_count && p.k1_finish_clamped && (!(span > 0.0) || nt == 1) && !(r2.flags & 8) && p.n_points >= 2) {
+      const double mup0 = level0_mup(mode, iso, p.k1_finish_clamped == 2, s_den[0], s_b[0], s_psi[0], f_hz);
+      if (!isinf(mup0)) {
+        p.vh[out_idx] = clamped_row_vh(mup0, span, s_alt[0], alt_min);
+        span = CUDART_NAN;                                                 // finished
+      }
+    }
+    p.row_span[lrow] = span;
+    if (p.live_count) append_live_rows(p, span == span, lrow, span);
     return;
   }
 
@@ -1426,6 +1482,7 @@ __device__ __noinline__ double const_mup_sum(const Node* nodes, const RowConst& 
       mup0 = ah_fast<MODE>(X, Y, sn, cs, nullptr);
     }
   }
+  if (mup0 != mup0) return 0.0;                           // every term NaN: nansum drops them all (lib:288)
   if (np >= 2 && isfinite(mup0)) {
     // mu' is one number, so the row's sum is mu' * sum(dh_i), and the weights telescope: dh_i = h_{i+1} - h_i
     // (lib:415) over [i0, i1) adds up to h(i1) - h(i0), plus the final 1e-6 (lib:416) in the row's last tile.  On the
@@ -1643,8 +1700,11 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   // every load of the prologue is independent of the others: issue them together
   const ProfileRecord rec = rec_src ? *rec_src : load_profile_record(p.prof_rec + lprof);
   const double f_mhz = src ? src->f_mhz : p.freq[prof * p.freq_stride + r];
-  const double m_lo = __ldg(p.mult + i0), m_hi = __ldg(p.mult + i1 - 1);
-  const double e_lo = __ldg(p.etab + i0), e_hi = __ldg(p.etab + i1 - 1);
+  // (a tile that is the whole row starts at m = 0, E = e^10 and ends at m = 1, E = 1: no table reads on its prologue)
+  const bool whole_row = (n_seg == 1) && p.n_points > 1;
+  const double m_lo = whole_row ? 0.0 : __ldg(p.mult + i0), m_hi = whole_row ? 1.0 : __ldg(p.mult + i1 - 1);
+  const double e_lo = whole_row ? 22026.465794806718 : __ldg(p.etab + i0);
+  const double e_hi = whole_row ? 1.0 : __ldg(p.etab + i1 - 1);
   if (!(span == span)) return;                            // no reflection / failed profile: K1 wrote the NaN
   PRHF_TRACE_MARK(3);
   const int nt = rec.nt;
@@ -1762,6 +1822,26 @@ __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char*
     }
   }
   const int n_tiles = live * n_seg;
+  if (p.queue_tickets) {
+    // Queued mode (large batches): tiles are handed out by ticket.  A static stride over the queue measured 11 % SLOWER
+    // than one CTA per row (profiles/queue_modes_r02.txt): with equal tiles per CTA the launch ends with its slowest SM,
+    // whereas the hardware's block scheduler -- and a ticket -- give a faster SM more tiles.  The ticket for the NEXT
+    // tile is drawn before the current one is computed, so its latency hides behind the grid loop.
+    __shared__ unsigned s_next;
+    unsigned t = blockIdx.x;
+    while (t < (unsigned)n_tiles) {
+      unsigned ticket = 0;
+      if (threadIdx.x == 0) ticket = atomicAdd(p.live_count + 1, 1u);
+      const unsigned li = t / (unsigned)n_seg;
+      const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
+      const double span = __hiloint2double(raw.w, raw.z);
+      tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, (int)(t - li * (unsigned)n_seg), n_seg, seg_len, smem_raw, sc);
+      if (threadIdx.x == 0) s_next = ticket + gridDim.x;
+      __syncthreads();                                    // also: shared memory is reused by the next tile
+      t = s_next;
+    }
+    return;
+  }
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int li = t / n_seg;
     // written earlier in this launch sequence (possibly in this very kernel): bypass L1

@@ -77,6 +77,8 @@ struct VfoParams {
   int rows_per_warp;       // K1: sounding frequencies handled by one warp (CTA = 8 warps)
   int k1_solo;             // row setup inside the solo kernel: one row per CTA, scanned by warp 0
   int k1_lane_mode;        // K1: one thread per sounding frequency (large batches) instead of one warp
+  int k1_finish_clamped;   // queued mode: K1 finishes rows clamped to the first level itself (1; 2 = literal arithmetic)
+  int queue_tickets;       // queued mode: tiles handed out by an atomic ticket (live_count[1]) instead of a static stride
   int rw_rows_per_cta;     // row-per-warp kernel: rows of one profile handled by one CTA
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null

@@ -1,6 +1,6 @@
 """Developer A/B of library builds on one box (not part of the product).
 
-usage: python tools/ab_tile.py libA.so libB.so ...     (paths relative to pyrayhf_b200/csrc)
+usage: python tools/ab_tile.py libA.so libB.so:PRHF_NO_QUEUE=1 ...     (paths relative to pyrayhf_b200/csrc)
 Every build runs the same cases in its own process (PRHF_LIB_PATH); timings are medians of CUDA-event timed calls with
 an L2 flush in between; the virtual heights of every case are compared with the first build's (NaN masks, max relative
 difference) and the first case is also compared with the scalar C oracle on two profiles.
@@ -57,10 +57,13 @@ def main():
     libs = sys.argv[1:]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     tags = []
-    for lib in libs:
-        tag = os.path.basename(lib).replace("libpyrayhf_b200", "").replace(".so", "") or "head"
+    for spec in libs:                                  # "lib.so" or "lib.so:ENV=VALUE[:ENV=VALUE]"
+        lib, *sets = spec.split(":")
+        tag = (os.path.basename(lib).replace("libpyrayhf_b200", "").replace(".so", "") or "head") + "".join(
+            "+" + kv.split("=")[0].replace("PRHF_", "").lower() for kv in sets)
         tags.append(tag)
         env = dict(os.environ, PRHF_LIB_PATH=os.path.join(ROOT, "pyrayhf_b200", "csrc", lib))
+        env.update(dict(kv.split("=", 1) for kv in sets))
         subprocess.run([sys.executable, __file__, "--child", tag], env=env, check=False, timeout=600)
     base = np.load(os.path.join(ROOT, "gpurun_out", "ab_%s.npz" % tags[0]))
     for tag in tags[1:]:
