@@ -2027,7 +2027,11 @@ __global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_solo_kernel(
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.freq + prof * p.freq_stride + lrow % p.n_freq));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mult + i0));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.mult + max(i1 - 1, i0)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.etab + max(i1 - 1, i0)));
     }
+    // the seeds of the E-space loop: one pair of table entries per thread, the tile's first 4 KB of E
+    if (threadIdx.x >= 32 && threadIdx.x < 64)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.etab + i0 + (threadIdx.x - 32) * 16));
     // the rows of a profile share the segment: each CTA requests only its own slice of the lines, so the segment
     // is pulled into L2 once instead of once per row
     // ... and the second line of the kernel parameters (cold constant bank), whose first reader would otherwise be
