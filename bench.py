@@ -236,7 +236,8 @@ def measured_peaks():
 
 
 def committed_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+    of this bench command, committed as profiles/traffic.json: {kernel: {"dram_bytes_per_launch": ...}}), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             return json.load(fh).get(kernel, {}).get("dram_bytes_per_launch")
@@ -430,8 +431,8 @@ def latency_block(torch, dev, stream, ctx, synth, flush, steps, warmup, clocks, 
     achieved = flops / (kernel_ms * 1e-3) / 1e12
     solo = launches == steps
     kname = "vfo_solo_kernel<1,0>" if solo else "vfo_tile_kernel<1,0>"
-    # inputs once (3 profile arrays + altitudes + frequencies), outputs, and the stretched-grid multiplier table
-    hbm_bytes = (4 * alt.size + freq.size) * 8 + 8 * freq.size + (N_POINTS + 4) * 8
+    # inputs once (3 profile arrays + altitudes + frequencies), outputs, and the stretched-grid tables (m, dm, E)
+    hbm_bytes = (4 * alt.size + freq.size) * 8 + 8 * freq.size + 3 * (N_POINTS + 4) * 8
     return {
         "workload": "BASELINE configs[1]: single synthetic Chapman day profile (lat 4.5, lon 0, dipole B), X-mode, "
                     "174 freqs 0.1-17.4 MHz, n_points=20000, 620 altitudes",
@@ -635,8 +636,9 @@ def run_b200_arm(args):
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     prof_per_launch = n_local / max(launches_per_step, 1)
     # per launch: the chunk's three profile arrays + its results + status, the shared altitude / frequency vectors and
-    # the stretched-grid multiplier table
-    hbm_bytes = prof_per_launch * (3 * alt.size * 8 + freq.size * 8 + 4) + (alt.size + freq.size) * 8 + (N_POINTS + 4) * 8
+    # the stretched-grid tables (m, dm, E: the grid loop itself reads only its seeds from E)
+    hbm_bytes = (prof_per_launch * (3 * alt.size * 8 + freq.size * 8 + 4) + (alt.size + freq.size) * 8 +
+                 3 * (N_POINTS + 4) * 8)
     kname = "vfo_tile_kernel<1,0>"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -654,7 +656,8 @@ def run_b200_arm(args):
         },
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": committed_traffic(kname),
-                     "kernel": "prhf::" + kname + " (one CTA per (profile, frequency) row; rank 0's shard)",
+                     "kernel": "prhf::" + kname + " (rows that reflect queued by the row-setup kernel, one CTA per "
+                               "resident slot drawing whole-row tiles by ticket; rank 0's shard)",
                      "kernel_ms": kernel_ms, "rows_kernel_ms": rows_ms / max(pairs, 1),
                      "launches_per_step_per_rank": launches_per_step,
                      "step_frac": (flops_shard / (total_ms / args.steps * 1e-3) / 1e12) / peak_tf,
