@@ -1668,11 +1668,13 @@ __device__ __forceinline__ void finish_tile(const VfoParams& p, BlockScratch& sc
   p.vh[out_idx] = total + alt_min;                        // lib:292
 }
 
-// Where a tile takes its profile levels and its frequency from when they are NOT the caller's global buffers: the
-// single-launch kernel keeps the profile it staged in shared memory (and may have received it as kernel parameters).
+// The single-launch kernel has the profile's raw levels in shared memory already (its row setup staged them in the
+// first 4 * n_alt doubles of the dynamic shared memory): the tile then builds its nodes from those instead of loading
+// the levels from global memory a second time, and puts the nodes behind them -- when the tile's window fits the
+// `upper_bytes` that are left (it does whenever the window is at most half the altitude grid; else global loads).
 struct TileSrc {
   const double *alt, *den, *b, *psi;
-  double f_mhz;
+  unsigned upper_off, upper_bytes;
 };
 
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
@@ -1699,7 +1701,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
   const int i1 = min(p.n_points, i0 + seg_len);
   // every load of the prologue is independent of the others: issue them together
   const ProfileRecord rec = rec_src ? *rec_src : load_profile_record(p.prof_rec + lprof);
-  const double f_mhz = src ? src->f_mhz : p.freq[prof * p.freq_stride + r];
+  const double f_mhz = p.freq[prof * p.freq_stride + r];
   // (a tile that is the whole row starts at m = 0, E = e^10 and ends at m = 1, E = 1: no table reads on its prologue)
   const bool whole_row = (n_seg == 1) && p.n_points > 1;
   const double m_lo = whole_row ? 0.0 : __ldg(p.mult + i0), m_hi = whole_row ? 1.0 : __ldg(p.mult + i1 - 1);
@@ -1711,10 +1713,10 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 
   const int path = select_path<LITERAL>(rec.flags);
   const int A = p.n_alt;
-  const double* g_den = src ? src->den : p.den + prof * A;
-  const double* g_b = src ? src->b : p.bmag + prof * A;
-  const double* g_psi = src ? src->psi : p.bpsi + prof * A;
-  const double* g_alt = src ? src->alt : p.alt + prof * p.alt_stride;
+  const double* g_den = p.den + prof * A;
+  const double* g_b = p.bmag + prof * A;
+  const double* g_psi = p.bpsi + prof * A;
+  const double* g_alt = p.alt + prof * p.alt_stride;
 
   RowConst rc;
   rc.g_alt = g_alt;
@@ -1780,7 +1782,15 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
   if (const_mup) space = kSpaceAlt;
-  stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads, span, space);
+  if (src && (size_t)n_stage * sizeof(Node) <= src->upper_bytes) {
+    // raw levels from shared memory, nodes behind them (single-launch kernel)
+    nodes = reinterpret_cast<Node*>(smem_raw + src->upper_off);
+    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, src->alt, src->den, src->b, src->psi, kx, ky, tid, kTileThreads,
+                span, space);
+  } else {
+    if (src) __syncthreads();                             // (every thread is done with the raw levels in shared memory)
+    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads, span, space);
+  }
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
@@ -2051,7 +2061,17 @@ __global__ void __launch_bounds__(kTileThreads, kSoloMinBlocks) vfo_solo_kernel(
   __syncthreads();
   const double span = s_span;
   if (!(span == span)) return;                            // no reflection / failed profile: NaN already written
-  tile_body<MODE, LITERAL>(p, lrow, span, &s_rec, (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc);
+  const size_t raw_bytes = sizeof(double) * 4 * (size_t)p.n_alt;
+  const size_t all_bytes = sizeof(Node) * (size_t)p.n_alt;             // the launcher grants max(5 n_alt doubles, this)
+  const double* raw = reinterpret_cast<const double*>(smem_raw);       // rows_body: den | alt | b | psi
+  TileSrc src;
+  src.den = raw;
+  src.alt = raw + p.n_alt;
+  src.b = raw + 2 * (size_t)p.n_alt;
+  src.psi = raw + 3 * (size_t)p.n_alt;
+  src.upper_off = (unsigned)raw_bytes;
+  src.upper_bytes = (unsigned)(all_bytes > raw_bytes ? all_bytes - raw_bytes : 0);
+  tile_body<MODE, LITERAL>(p, lrow, span, &s_rec, (int)(tile % p.n_seg), p.n_seg, p.seg_len, smem_raw, sc, &src);
 }
 
 // ------------------------------------------------------------------------------------------
