@@ -1677,12 +1677,22 @@ struct TileSrc {
   unsigned upper_off, upper_bytes;
 };
 
+// Queued mode: the end of a whole-row tile in ONE barrier.  The warps leave their partial sums in `part` (the caller
+// alternates two buffers from tile to tile), thread 0 publishes the next tile's index alongside, and after the barrier
+// thread 0 alone adds the partials in warp order (deterministic) and writes the row while the other warps are already
+// in the next tile's prologue.  The general finish_tile costs two barriers plus the caller's end-of-tile barrier.
+struct QueueFinish {
+  double* part;            // [kMaxWarps]
+  unsigned* next_slot;     // shared word the tile loop reads its next index from
+  unsigned next_value;     // valid in thread 0
+};
+
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
 template <int MODE, bool LITERAL>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
                                           const ProfileRecord* rec_src, const int seg, const int n_seg,
                                           const int seg_len, unsigned char* smem_raw, BlockScratch& sc,
-                                          const TileSrc* src = nullptr) {
+                                          const TileSrc* src = nullptr, const QueueFinish* qf = nullptr) {
   const int tid = threadIdx.x;
 #ifdef PRHF_TRACE
   if (p.trace && tid == 0) {
@@ -1804,6 +1814,20 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
                                                       st, space, i0, i1, p.n_points);
 
   // ---- reduce, finish (lib:288-292) ----
+  if (qf) {                                               // queued mode, n_seg == 1
+    const double w = warp_sum(acc);
+    if ((tid & 31) == 0) qf->part[tid >> 5] = w;
+    if (tid == 0) *qf->next_slot = qf->next_value;
+    __syncthreads();
+    if (tid == 0) {
+      double total = 0.0;
+#pragma unroll
+      for (int k = 0; k < kTileThreads / 32; ++k) total += qf->part[k];
+      if (total == 0.0) total = CUDART_NAN;               // lib:290
+      p.vh[prof * p.n_freq + r] = total + rec.alt_min;    // lib:292
+    }
+    return;
+  }
   finish_tile(p, sc, acc, lrow, seg, n_seg, prof * p.n_freq + r, rec.alt_min);
 }
 
@@ -1838,16 +1862,26 @@ __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char*
     // whereas the hardware's block scheduler -- and a ticket -- give a faster SM more tiles.  The ticket for the NEXT
     // tile is drawn before the current one is computed, so its latency hides behind the grid loop.
     __shared__ unsigned s_next;
-    unsigned t = blockIdx.x;
+    __shared__ double s_part[2][kMaxWarps];
+    unsigned t = blockIdx.x, flip = 0;
     while (t < (unsigned)n_tiles) {
       unsigned ticket = 0;
       if (threadIdx.x == 0) ticket = atomicAdd(p.live_count + 1, 1u);
       const unsigned li = t / (unsigned)n_seg;
       const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
       const double span = __hiloint2double(raw.w, raw.z);
-      tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, (int)(t - li * (unsigned)n_seg), n_seg, seg_len, smem_raw, sc);
-      if (threadIdx.x == 0) s_next = ticket + gridDim.x;
-      __syncthreads();                                    // also: shared memory is reused by the next tile
+      if (n_seg == 1) {
+        QueueFinish qf;
+        qf.part = s_part[flip];
+        qf.next_slot = &s_next;
+        qf.next_value = ticket + gridDim.x;
+        flip ^= 1u;
+        tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, 0, 1, seg_len, smem_raw, sc, nullptr, &qf);
+      } else {
+        tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, (int)(t - li * (unsigned)n_seg), n_seg, seg_len, smem_raw, sc);
+        if (threadIdx.x == 0) s_next = ticket + gridDim.x;
+        __syncthreads();                                  // also: shared memory is reused by the next tile
+      }
       t = s_next;
     }
     return;
