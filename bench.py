@@ -639,7 +639,7 @@ def run_b200_arm(args):
     # the stretched-grid tables (m, dm, E: the grid loop itself reads only its seeds from E)
     hbm_bytes = (prof_per_launch * (3 * alt.size * 8 + freq.size * 8 + 4) + (alt.size + freq.size) * 8 +
                  3 * (N_POINTS + 4) * 8)
-    kname = "vfo_tile_kernel<1,0>"
+    kname = "vfo_queue_kernel<1,0>"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -656,8 +656,8 @@ def run_b200_arm(args):
         },
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": committed_traffic(kname),
-                     "kernel": "prhf::" + kname + " (rows that reflect queued by the row-setup kernel, one CTA per "
-                               "resident slot drawing whole-row tiles by ticket; rank 0's shard)",
+                     "kernel": "prhf::" + kname + " (rows that reflect queued by the row-setup kernel; 128-thread CTAs, "
+                               "one per resident slot, eight per SM, drawing whole-row tiles by ticket; rank 0's shard)",
                      "kernel_ms": kernel_ms, "rows_kernel_ms": rows_ms / max(pairs, 1),
                      "launches_per_step_per_rank": launches_per_step,
                      "step_frac": (flops_shard / (total_ms / args.steps * 1e-3) / 1e12) / peak_tf,

@@ -62,9 +62,8 @@ struct prhf_ctx {
   bool use_rowwarp = true;           // PRHF_NO_ROWWARP=1: small n_points through the tile kernel
   int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
-  int queue_mode = 2;                // PRHF_QUEUE: 0 large batches with one tile-kernel CTA per row (no live-row queue),
-                                     // 1 queue + static stride (slower: measurement only), 2 queue + tickets
-  prhf::LiveRow* live_list = nullptr;
+  int queue_mode = 1;                // PRHF_QUEUE=0: large batches with one tile-kernel CTA per row (no live-row queue)
+  prhf::LiveRow* live_list = nullptr;     // [2 x live_list_cap]: the queue, then the rows deferred to the full-width kernel
   size_t live_list_cap = 0;
   void* node_table = nullptr;        // un-scaled nodes of profiles too long for shared memory (n_alt > prhf_max_n_alt)
   size_t node_table_cap = 0;
@@ -180,7 +179,7 @@ int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
     if (ctx->live_list) cudaFree(ctx->live_list);
     ctx->live_list = nullptr;
     ctx->live_list_cap = 0;
-    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_list, sizeof(prhf::LiveRow) * n_rows));
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->live_list, sizeof(prhf::LiveRow) * 2 * n_rows));
     ctx->live_list_cap = n_rows;
     ctx->epoch++;
   }
@@ -506,8 +505,8 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
   // kernel runs one CTA per resident slot and strides over the queue.  Against one CTA per row this drops the launch of
   // a CTA for every row that does not reflect (two of three on a global grid) and keeps every queued row equally long.
   const bool lane_k1 = !planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count;
-  const bool queued = !solo && !planned && !big && lane_k1 && ctx->queue_mode > 0 &&
-                      !(n_seg == 1 && n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp);
+  const bool queued = !solo && !planned && !big && lane_k1 && ctx->queue_mode > 0 && n_seg == 1 &&
+                      !(n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp);
   if (queued) {
     n_cand = 1;
     cand_seg[0] = n_seg;
@@ -552,7 +551,8 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     P.k1_solo = solo ? 1 : 0;
     P.k1_lane_mode = lane_k1 ? 1 : 0;
     P.k1_finish_clamped = queued ? (literal ? 2 : 1) : 0;
-    P.queue_tickets = (queued && ctx->queue_mode >= 2) ? 1 : 0;
+    P.queue_cap_nodes = queued ? prhf::vfo_queue_cap_nodes(n_alt, ctx->max_smem_per_sm) : 0;
+    P.defer_list = queued ? ctx->live_list + ctx->live_list_cap : nullptr;
     P.vh = vh_out;
     P.status = status;
     P.prof_rec = ctx->prof_rec;
@@ -563,7 +563,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
     if (planned || queued) {
       // the live-row counter starts every launch at zero (a 4-byte memset node: simpler and safer than any
       // hand-over of the reset between consecutive calls)
-      PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, 2 * sizeof(unsigned), stream));   // [live rows, tickets]
+      PRHF_CUDA(ctx, cudaMemsetAsync(ctx->live_count, 0, 4 * sizeof(unsigned), stream));   // [live rows, tickets, deferred rows]
       P.live_count = ctx->live_count;
       P.live_list = ctx->live_list;
     } else {
@@ -638,9 +638,24 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       P.rw_rows_per_cta = n_freq;
     }
     // planned mode: enough CTAs for two waves of slots; they stride over however many tiles K1 planned
-    const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots)
-                       : queued  ? std::min<int64_t>(np * tiles_per_profile, (int64_t)slots)
-                                 : np * tiles_per_profile;
+    const int64_t grid = planned ? std::min<int64_t>(np * tiles_per_profile, (int64_t)2 * slots) : np * tiles_per_profile;
+    // queued mode: the narrow kernel (one CTA per slot, eight slots per SM, tickets) over the queue, then the full-width
+    // kernel over the rows the narrow one deferred (window larger than its node buffer; usually none: the launch is a
+    // few microseconds of CTAs that read a zero and leave)
+    auto launch_queued = [&]() -> int {
+      prhf::VfoParams Q = P;
+      const double step = (n_points > 1) ? 10.0 / (double)(n_points - 1) : 0.0;
+      Q.e_ratio = std::exp(-step * (double)(2 * prhf::vfo_queue_threads()));
+      const int64_t q_slots = (int64_t)ctx->sm_count * prhf::vfo_queue_ctas_per_sm();
+      PRHF_CUDA(ctx, prhf::launch_vfo_queue(Q, mode, literal, std::min<int64_t>(np * (int64_t)n_freq, q_slots), stream));
+      prhf::VfoParams D = P;
+      D.live_count = ctx->live_count + 2;
+      D.live_list = P.defer_list;
+      D.use_pdl = 0;
+      PRHF_CUDA(ctx, prhf::launch_vfo_tiles(D, mode, literal, std::min<int64_t>(np * (int64_t)n_freq, (int64_t)slots), stream));
+      ctx->launches += 1;                                     // (the row-setup + first tile launch are counted by the caller)
+      return PRHF_OK;
+    };
     if (rowwarp && !ctx->kernel_timing) {
       PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
       PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));
@@ -654,6 +669,7 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
       PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
       if (rowwarp) PRHF_CUDA(ctx, prhf::launch_vfo_rowwarp(P, mode, literal, rw_ctas, stream));
+      else if (queued) { rc = launch_queued(); if (rc != PRHF_OK) return rc; }
       else PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
       PRHF_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
       PRHF_CUDA(ctx, cudaEventSynchronize(ctx->ev[2]));
@@ -667,7 +683,8 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
       continue;
     }
     PRHF_CUDA(ctx, prhf::launch_vfo_rows(P, mode, np, stream));
-    PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
+    if (queued) { rc = launch_queued(); if (rc != PRHF_OK) return rc; }
+    else PRHF_CUDA(ctx, prhf::launch_vfo_tiles(P, mode, literal, grid, stream));
     ctx->launches += 2;
   }
   return PRHF_OK;
@@ -899,7 +916,20 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
   }
   if (per_prof > 0) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)(((size_t)512 << 20) / per_prof)));
   chunk = std::min<int64_t>(chunk, n_profiles);
-  const int64_t n_chunks = (n_profiles + chunk - 1) / chunk;
+  // Chunk boundaries.  The copy-in of the FIRST chunk is the one copy nothing can hide, so (unless the caller fixed the
+  // chunk size) the call opens with a quarter-size chunk: 0.3 ms instead of 1.1 ms of exposed PCIe time per call at
+  // 4096 profiles per chunk, and the kernels of that short chunk already cover the copy-in of the next, full one.
+  std::vector<int64_t> starts;
+  {
+    int64_t p = 0;
+    if (chunk_profiles == 0 && per_prof > 0 && n_profiles > chunk && chunk >= 1024) {
+      starts.push_back(0);
+      p = chunk / 4;
+    }
+    for (; p < n_profiles; p += chunk) starts.push_back(p);
+    starts.push_back(n_profiles);
+  }
+  const int64_t n_chunks = (int64_t)starts.size() - 1;
 
   // resources: streams, events, two staging slots, device copies of shared host vectors
   if (!ctx->s_in) {
@@ -977,7 +1007,7 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
   // never sit behind them in a hardware queue two streams happen to share.
   auto issue_copy_in = [&](int64_t c) -> int {
     const int slot = (int)(c & 1);
-    const int64_t p0 = c * chunk, np = std::min(chunk, n_profiles - p0);
+    const int64_t p0 = starts[c], np = starts[c + 1] - p0;
     char* base = ctx->slot_buf[slot];
     size_t off = 0;
     auto carve = [&](size_t bytes) {
@@ -1023,7 +1053,7 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
   if (rc != PRHF_OK) return rc;
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int slot = (int)(c & 1);
-    const int64_t p0 = c * chunk, np = std::min(chunk, n_profiles - p0);
+    const int64_t p0 = starts[c], np = starts[c + 1] - p0;
     if (c + 1 < n_chunks) {
       rc = issue_copy_in(c + 1);
       if (rc != PRHF_OK) return rc;

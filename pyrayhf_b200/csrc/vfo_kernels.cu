@@ -1685,10 +1685,13 @@ struct QueueFinish {
   double* part;            // [kMaxWarps]
   unsigned* next_slot;     // shared word the tile loop reads its next index from
   unsigned next_value;     // valid in thread 0
+  int cap_nodes;           // levels the CTA's node buffer holds; a row whose window is larger is deferred:
+  unsigned* defer_count;   // ... appended to this list for the full-width kernel that follows
+  LiveRow* defer_list;
 };
 
 // One tile: grid points [seg * seg_len, (seg+1) * seg_len) of row `lrow`.
-template <int MODE, bool LITERAL>
+template <int MODE, bool LITERAL, int NT = kTileThreads>
 __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow, const double span,
                                           const ProfileRecord* rec_src, const int seg, const int n_seg,
                                           const int seg_len, unsigned char* smem_raw, BlockScratch& sc,
@@ -1774,7 +1777,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
       }
 #endif
     } else {
-      if (tid == 0 || tid == 32) {                        // kTileThreads >= 64
+      if (tid == 0 || tid == 32) {                        // NT >= 64
         const double h = (tid == 0) ? h_lo : h_hi;
         const int gj = (tid == 0) ? g_lo : g_hi;
         int j;
@@ -1792,21 +1795,34 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
 
   Node* nodes = reinterpret_cast<Node*>(smem_raw);
   if (const_mup) space = kSpaceAlt;
+  if (qf && qf->cap_nodes > 0 && n_stage > qf->cap_nodes) {
+    // narrow queue kernel: the row's window does not fit this CTA's node buffer -- hand the row to the full-width
+    // kernel that follows (rows that reflect in the upper half of a long altitude grid; block-uniform decision)
+    if (tid == 0) {
+      LiveRow e;
+      e.row = (int)lrow;
+      e.pad = 0;
+      e.span = span;
+      qf->defer_list[atomicAdd(qf->defer_count, 1u)] = e;
+      *qf->next_slot = qf->next_value;
+    }
+    __syncthreads();
+    return;
+  }
   if (src && (size_t)n_stage * sizeof(Node) <= src->upper_bytes) {
     // raw levels from shared memory, nodes behind them (single-launch kernel)
     nodes = reinterpret_cast<Node*>(smem_raw + src->upper_off);
-    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, src->alt, src->den, src->b, src->psi, kx, ky, tid, kTileThreads,
-                span, space);
+    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, src->alt, src->den, src->b, src->psi, kx, ky, tid, NT, span, space);
   } else {
     if (src) __syncthreads();                             // (every thread is done with the raw levels in shared memory)
-    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, kTileThreads, span, space);
+    stage_nodes(nodes, rc.jlo, n_stage, nt, path, rec, g_alt, g_den, g_b, g_psi, kx, ky, tid, NT, span, space);
   }
   __syncthreads();
   PRHF_TRACE_MARK(5);
 
   // ---- grid points of the tile ----
   rc.lane0 = tid;
-  rc.group = kTileThreads;
+  rc.group = NT;
   rc.kx = kx;
   rc.ky = ky;
   const StretchTables st{p.mult, p.dmult, p.etab, p.e_ratio, p.e_weight};
@@ -1822,7 +1838,7 @@ __device__ __forceinline__ void tile_body(const VfoParams& p, const int64_t lrow
     if (tid == 0) {
       double total = 0.0;
 #pragma unroll
-      for (int k = 0; k < kTileThreads / 32; ++k) total += qf->part[k];
+      for (int k = 0; k < NT / 32; ++k) total += qf->part[k];
       if (total == 0.0) total = CUDART_NAN;               // lib:290
       p.vh[prof * p.n_freq + r] = total + rec.alt_min;    // lib:292
     }
@@ -1856,36 +1872,6 @@ __device__ __forceinline__ void planned_tiles(const VfoParams& p, unsigned char*
     }
   }
   const int n_tiles = live * n_seg;
-  if (p.queue_tickets) {
-    // Queued mode (large batches): tiles are handed out by ticket.  A static stride over the queue measured 11 % SLOWER
-    // than one CTA per row (profiles/queue_modes_r02.txt): with equal tiles per CTA the launch ends with its slowest SM,
-    // whereas the hardware's block scheduler -- and a ticket -- give a faster SM more tiles.  The ticket for the NEXT
-    // tile is drawn before the current one is computed, so its latency hides behind the grid loop.
-    __shared__ unsigned s_next;
-    __shared__ double s_part[2][kMaxWarps];
-    unsigned t = blockIdx.x, flip = 0;
-    while (t < (unsigned)n_tiles) {
-      unsigned ticket = 0;
-      if (threadIdx.x == 0) ticket = atomicAdd(p.live_count + 1, 1u);
-      const unsigned li = t / (unsigned)n_seg;
-      const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + li));
-      const double span = __hiloint2double(raw.w, raw.z);
-      if (n_seg == 1) {
-        QueueFinish qf;
-        qf.part = s_part[flip];
-        qf.next_slot = &s_next;
-        qf.next_value = ticket + gridDim.x;
-        flip ^= 1u;
-        tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, 0, 1, seg_len, smem_raw, sc, nullptr, &qf);
-      } else {
-        tile_body<MODE, LITERAL>(p, raw.x, span, nullptr, (int)(t - li * (unsigned)n_seg), n_seg, seg_len, smem_raw, sc);
-        if (threadIdx.x == 0) s_next = ticket + gridDim.x;
-        __syncthreads();                                  // also: shared memory is reused by the next tile
-      }
-      t = s_next;
-    }
-    return;
-  }
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int li = t / n_seg;
     // written earlier in this launch sequence (possibly in this very kernel): bypass L1
@@ -1921,6 +1907,45 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
     return;
   }
   planned_tiles<MODE, LITERAL>(p, smem_raw, sc);
+}
+
+// Queued mode (large batches): one CTA per resident slot draws whole-row tiles from the queue the row setup filled.
+// * Tiles are handed out by ticket.  A static stride over the queue measured 11 % SLOWER than one CTA per row
+//   (profiles/queue_modes_r02.txt): with equal tile counts the launch ends with its slowest SM, whereas the hardware's
+//   block scheduler -- and a ticket -- give a faster SM more tiles.  The ticket for the NEXT tile is drawn before the
+//   current one is computed, so its latency hides behind the grid loop.
+// * Narrow CTAs: 128 threads, eight CTAs per SM instead of four of 256.  A tile is a whole row either way, so the
+//   per-tile prologue and the barriers at its ends cost the same number of cycles but half the share of a CTA's
+//   residency, and a CTA in its prologue idles 4 warps of 32 instead of 8 (+3 %, profiles/queue_modes_r02.txt).  Eight
+//   CTAs leave each of them p.queue_cap_nodes levels of node buffer (434 on B200); a row whose window is larger is
+//   deferred to the full-width kernel, launched behind this one over the deferred list.
+constexpr int kQueueThreads = 128;
+constexpr int kQueueMinBlocks = 8;
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(kQueueThreads, kQueueMinBlocks) vfo_queue_kernel(const VfoParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockScratch sc;
+  __shared__ unsigned s_next;
+  __shared__ double s_part[2][kMaxWarps];
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the row-setup grid has completed (no-op without PDL)
+  const unsigned n_tiles = __ldcg(p.live_count);
+  unsigned t = blockIdx.x, flip = 0;
+  while (t < n_tiles) {
+    unsigned ticket = 0;
+    if (threadIdx.x == 0) ticket = atomicAdd(p.live_count + 1, 1u);
+    const int4 raw = __ldcg(reinterpret_cast<const int4*>(p.live_list + t));
+    const double span = __hiloint2double(raw.w, raw.z);
+    QueueFinish qf;
+    qf.part = s_part[flip];
+    qf.next_slot = &s_next;
+    qf.next_value = ticket + gridDim.x;
+    qf.cap_nodes = p.queue_cap_nodes;
+    qf.defer_count = p.live_count + 2;
+    qf.defer_list = p.defer_list;
+    flip ^= 1u;
+    tile_body<MODE, LITERAL, kQueueThreads>(p, raw.x, span, nullptr, 0, 1, p.n_points, smem_raw, sc, nullptr, &qf);
+    t = s_next;
+  }
 }
 
 // Row-per-warp form for small n_points (direct mode): one CTA stages the profile's levels ONCE (un-scaled)
@@ -2366,6 +2391,42 @@ static cudaError_t launch_tiles(const VfoParams& p, int64_t n_tiles, cudaStream_
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream) {
   if (mode == 0) return literal ? launch_tiles<0, true>(p, n_tiles, stream) : launch_tiles<0, false>(p, n_tiles, stream);
   return literal ? launch_tiles<1, true>(p, n_tiles, stream) : launch_tiles<1, false>(p, n_tiles, stream);
+}
+
+int vfo_queue_ctas_per_sm() { return kQueueMinBlocks; }
+int vfo_queue_threads() { return kQueueThreads; }
+// levels of node buffer each of the eight CTAs of an SM can have (1 KB per CTA is reserved by the driver, ~0.5 KB static)
+int vfo_queue_cap_nodes(int n_alt, int max_smem_per_sm) {
+  const int by_smem = (int)(((size_t)max_smem_per_sm / kQueueMinBlocks - 1024 - 512) / sizeof(Node));
+  return by_smem < n_alt ? (by_smem < 0 ? 0 : by_smem) : n_alt;
+}
+
+template <int MODE, bool LITERAL>
+static cudaError_t launch_queue_t(const VfoParams& p, int64_t n_ctas, cudaStream_t stream) {
+  const size_t smem = sizeof(Node) * (size_t)p.queue_cap_nodes;
+  auto kern = vfo_queue_kernel<MODE, LITERAL>;
+  cudaError_t e = grant_dynamic_smem((const void*)kern, 5 + MODE * 2 + (LITERAL ? 1 : 0), smem);
+  if (e != cudaSuccess) return e;
+  if (!p.use_pdl) {
+    kern<<<(unsigned)n_ctas, kQueueThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(kQueueThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+cudaError_t launch_vfo_queue(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream) {
+  if (mode == 0) return literal ? launch_queue_t<0, true>(p, n_ctas, stream) : launch_queue_t<0, false>(p, n_ctas, stream);
+  return literal ? launch_queue_t<1, true>(p, n_ctas, stream) : launch_queue_t<1, false>(p, n_ctas, stream);
 }
 
 template <int MODE, bool LITERAL>

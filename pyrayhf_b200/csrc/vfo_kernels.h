@@ -78,7 +78,9 @@ struct VfoParams {
   int k1_solo;             // row setup inside the solo kernel: one row per CTA, scanned by warp 0
   int k1_lane_mode;        // K1: one thread per sounding frequency (large batches) instead of one warp
   int k1_finish_clamped;   // queued mode: K1 finishes rows clamped to the first level itself (1; 2 = literal arithmetic)
-  int queue_tickets;       // queued mode: tiles handed out by an atomic ticket (live_count[1]) instead of a static stride
+  int queue_cap_nodes;     // queued mode: levels of node buffer per CTA of the narrow kernel (live_count[1] = tickets,
+                           // live_count[2] = rows deferred to the full-width kernel because their window is larger)
+  LiveRow* defer_list;     // [rows_in_launch]
   int rw_rows_per_cta;     // row-per-warp kernel: rows of one profile handled by one CTA
   double* vh;              // [P x n_freq]
   int* status;             // [P] or null
@@ -117,6 +119,10 @@ cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cu
 cudaError_t launch_vfo_tiles(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
 cudaError_t launch_vfo_rowwarp(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
 cudaError_t launch_vfo_solo(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);
+cudaError_t launch_vfo_queue(const VfoParams& p, int mode, bool literal, int64_t n_ctas, cudaStream_t stream);
+int vfo_queue_ctas_per_sm();
+int vfo_queue_threads();
+int vfo_queue_cap_nodes(int n_alt, int max_smem_per_sm);
 size_t vfo_node_bytes();
 cudaError_t launch_vfo_nodes_global(const VfoParams& p, bool literal, int64_t n_profiles, cudaStream_t stream);
 cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, int64_t n_tiles, cudaStream_t stream);

@@ -4,8 +4,10 @@ reads), the live-row queue of large batches, and the rows the row setup finishes
 * odd / even n_points, tile boundaries and re-seed boundaries of the E-space loop against the scalar C restatement of
   library.py:459-509 (X-mode) and the long-double truth (O-mode) -- the last pair of points of a row is added outside
   the loop and differs between odd and even n_points;
-* queued mode (PRHF_QUEUE=2, default) == one tile-kernel CTA per row (PRHF_QUEUE=0), bit for bit, on a batch that has
-  rows without reflection, rows clamped to the first level (finished by the row setup in queued mode) and ordinary rows.
+* queued mode (default: narrow CTAs drawing whole rows by ticket) against one full-width tile-kernel CTA per row
+  (PRHF_QUEUE=0) on a batch that has rows without reflection, rows clamped to the first level (finished by the row
+  setup in queued mode) and ordinary rows; rows whose level window exceeds the narrow kernel's node buffer are deferred
+  to the full-width kernel.
 """
 import numpy as np
 import pytest
@@ -64,7 +66,8 @@ def test_espace_loop_small_batches(mode, n_points, n_prof):
 def test_queued_mode_equals_one_cta_per_row(mode, literal, n_points, f_step, monkeypatch):
     """>= 148 profiles and more than 4096 grid points per row: the row setup (one thread per frequency) queues the rows
     that reflect and finishes the rows clamped to the first level in closed form; PRHF_QUEUE=0 is the round-1 form
-    with one tile-kernel CTA per row.  Same bits; oracle on sampled profiles."""
+    with one full-width tile-kernel CTA per row.  Same masks and status, values to 1e-12 (128 against 256 threads per
+    tile), clamped rows bit for bit; oracle on sampled profiles."""
     import torch
     import pyrayhf_b200 as prhf
     from pyrayhf_b200 import _cabi, synth
@@ -87,10 +90,50 @@ def test_queued_mode_equals_one_cta_per_row(mode, literal, n_points, f_step, mon
     monkeypatch.setattr(_cabi, "_contexts", {})
     b, sb = run()
     assert np.array_equal(sa, sb) and sa[7] == 2 and sa[11] == 1 and np.count_nonzero(sa) == 2
-    assert np.array_equal(a, b, equal_nan=True)
+    # same rows, other thread count per tile (128 against 256): the sums associate differently
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = np.isfinite(a)
+    assert np.max(np.abs(a[m] - b[m]) / np.abs(b[m])) < 1e-12
+    # rows clamped to the first level are finished by the row setup in queued mode and by the tile kernel otherwise:
+    # the same closed form, the same bits
+    clamped = m & (np.abs(a - alt.min()) < 1e-9)
+    assert np.array_equal(a[clamped], b[clamped])
     assert np.isnan(a[7]).all() and np.isnan(a[11]).all()
     if not literal:
         sample = [0, 150, 299]
         lit, tru = _truth_and_literal(freq, den[sample], bmag[sample], bpsi[sample], alt, mode, n_points)
         for k, q in enumerate(sample):
             assert_parity(a[q], lit[k], tru[k], mode, "queued %s profile %d" % (mode, q))
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_queued_mode_defers_rows_whose_window_exceeds_the_node_buffer(mode, monkeypatch):
+    """A 1 500-level altitude grid (0.41 km spacing): the narrow queue kernel holds 434 levels per CTA on B200, so every
+    row that reflects above ~260 km is deferred to the full-width kernel that follows; rows below it stay.  Against
+    the one-CTA-per-row form and the oracle."""
+    import torch
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import _cabi, synth
+    alt = np.linspace(80.0, 699.0, 1500)
+    freq = synth.default_freq()[::2]
+    lat, lon = synth.grid_subset(160)
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    assert den.argmax(axis=1).max() > 470                    # windows beyond the narrow kernel's buffer exist
+    n_points = 6000
+    dev = torch.device("cuda:0")
+
+    def run():
+        t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+        return prhf.vertical_forward_operator_batched(*t, mode, n_points).cpu().numpy()
+
+    a = run()
+    monkeypatch.setenv("PRHF_QUEUE", "0")
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    b = run()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = np.isfinite(a)
+    assert m.sum() > 1000 and np.max(np.abs(a[m] - b[m]) / np.abs(b[m])) < 1e-12
+    sample = [0, 80, 159]
+    lit, tru = _truth_and_literal(freq, den[sample], bmag[sample], bpsi[sample], alt, mode, n_points)
+    for k, q in enumerate(sample):
+        assert_parity(a[q], lit[k], tru[k], mode, "deferred rows %s profile %d" % (mode, q))
