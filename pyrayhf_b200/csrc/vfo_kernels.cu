@@ -1919,8 +1919,14 @@ __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks) vfo_tile_kernel(
 //   residency, and a CTA in its prologue idles 4 warps of 32 instead of 8 (+3 %, profiles/queue_modes_r02.txt).  Eight
 //   CTAs leave each of them p.queue_cap_nodes levels of node buffer (434 on B200); a row whose window is larger is
 //   deferred to the full-width kernel, launched behind this one over the deferred list.
-constexpr int kQueueThreads = 128;
-constexpr int kQueueMinBlocks = 8;
+#ifndef PRHF_QUEUE_THREADS
+#define PRHF_QUEUE_THREADS 128
+#endif
+#ifndef PRHF_QUEUE_MINB
+#define PRHF_QUEUE_MINB 8
+#endif
+constexpr int kQueueThreads = PRHF_QUEUE_THREADS;         // (developer builds: make ab NAME=.. DEFS="-DPRHF_QUEUE_MINB=10")
+constexpr int kQueueMinBlocks = PRHF_QUEUE_MINB;
 template <int MODE, bool LITERAL>
 __global__ void __launch_bounds__(kQueueThreads, kQueueMinBlocks) vfo_queue_kernel(const VfoParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
