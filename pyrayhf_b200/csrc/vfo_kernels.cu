@@ -1032,6 +1032,18 @@ __device__ __forceinline__ int find_bracket_pos(double h, const Node* nodes, int
 template <int PATH, bool ROWSCALE>
 __device__ __forceinline__ void fast_xy_node(double h, const Node& nd, const RowConst& rc, double* X_out,
                                              double* yth_out, double* yl_out);
+// E-space nodes of the constant-angle path hold intercepts and slopes (stage_nodes): one FMA per interpolant.
+template <int PATH>
+__device__ __forceinline__ void espace_xy_node(double E, const Node& nd, const RowConst& rc, double* X_out,
+                                               double* yth_out, double* yl_out) {
+  if (PATH == kPathFast0) {
+    *X_out = fma(nd.x, E, nd.alt);
+    *yth_out = fma(nd.y, E, nd.sx);
+    *yl_out = fma(nd.srad, E, nd.sy);
+  } else {
+    fast_xy_node<PATH, false>(E, nd, rc, X_out, yth_out, yl_out);
+  }
+}
 template <int PATH, bool ROWSCALE, bool ABS = false>
 __device__ __forceinline__ void fast_xy(double h, int j, const Node* nodes, const RowConst& rc, double* X_out,
                                         double* yth_out, double* yl_out) {
@@ -1376,7 +1388,7 @@ __device__ __noinline__ double near_reflection_tail_e(const Node* nodes, const R
           const int k = 2 * ip + u;
           const int j = bracket_floor_e(E[u], br);
           double X, yth, yl, mu, q;
-          fast_xy<PATH, false, true>(E[u], j, nb, rc, &X, &yth, &yl);
+          espace_xy_node<PATH>(E[u], nb[j], rc, &X, &yth, &yl);
           if (!near_reflection(X)) continue;
           const double p = ah_hot<0>(literal_x(__ldg(m + k), j, rc), yth, yl, &mu, &q);
           acc = fma(keep_term(p, q) ? p : 0.0, __ldg(dm + k) * rc.span, acc);
@@ -1412,8 +1424,8 @@ __device__ __forceinline__ double tile_sum_fast_e(const Node* nodes, const RowCo
       const Node& n0 = *reinterpret_cast<const Node*>(nb_bytes + bracket_bytes_e(E0, br));
       const Node& n1 = *reinterpret_cast<const Node*>(nb_bytes + bracket_bytes_e(E1, br));
       double X0, X1, yth0, yth1, yl0, yl1, mu0, mu1, q0, q1;
-      fast_xy_node<PATH, false>(E0, n0, rc, &X0, &yth0, &yl0);
-      fast_xy_node<PATH, false>(E1, n1, rc, &X1, &yth1, &yl1);
+      espace_xy_node<PATH>(E0, n0, rc, &X0, &yth0, &yl0);
+      espace_xy_node<PATH>(E1, n1, rc, &X1, &yth1, &yl1);
       const bool near0 = (MODE == 0) && near_reflection(X0), near1 = (MODE == 0) && near_reflection(X1);
       const double p0 = ah_hot<MODE>(X0, yth0, yl0, &mu0, &q0);
       const double p1 = ah_hot<MODE>(X1, yth1, yl1, &mu1, &q1);
@@ -1443,7 +1455,7 @@ __device__ __forceinline__ double tile_sum_fast_e(const Node* nodes, const RowCo
       const double Ek = __ldg(etab + k);
       const int jk = min(max(bracket_floor_e(Ek, br), rc.jlo), rc.jhi);
       double Xk, ythk, ylk, muk, qk;
-      fast_xy<PATH, false>(Ek, jk, nodes, rc, &Xk, &ythk, &ylk);
+      espace_xy_node<PATH>(Ek, nodes[jk - rc.jlo], rc, &Xk, &ythk, &ylk);
       // (coarse grids: the last point is the only one this close, and with its weight of 1e-6 km an ulp of X is worth
       //  < 1e-11 of the virtual height -- not worth an IEEE sqrt and two divisions on one lane of a 200-point row)
       if (MODE == 0 && (k < il || n_points >= 1024) && near_reflection(Xk)) Xk = literal_x(__ldg(m + k), jk, rc);
@@ -1605,6 +1617,26 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
         nd.srad = y0 * cc;
         nd.sn = sy0 * cc;
         nd.cs = 0.0;
+        if (space == kSpaceE) {
+          // E-space, constant field angle: intercept form.  The three interpolants become ONE FMA each on E itself,
+          // v(E) = v_j + s (E - E_j) = (v_j - s E_j) + s E, which drops the subtraction t = E - E_j from every grid point.
+          // Safe here and only here: the intercept differs from v_j by |s E_j|, and in E-space that product is small
+          // exactly where the integrand is sensitive -- E_j <= ~100 in the segment below the reflection level, which
+          // holds half of the row's points (B |dX/dm| E_j ~ 5e-3 against X ~ 1) -- while at the bottom of the row, where
+          // it reaches |dX/dm| ~ 1, mu' ~ 1 is insensitive to an X off by 1e-16.  Layout (three aligned LDS.128):
+          // {alt, x} = {X intercept, X slope}, {sx, y} = {YTh intercept, slope}, {sy, srad} = {YL intercept, slope}.
+          const double ej = nd.alt;
+          Node q;
+          q.alt = fma(-nd.sx, ej, nd.x);
+          q.x = nd.sx;
+          q.sx = fma(-nd.sy, ej, nd.y);
+          q.y = nd.sy;
+          q.sy = fma(-nd.sn, ej, nd.srad);
+          q.srad = nd.sn;
+          q.sn = ej;                                      // (kept for inspection; the loop does not read it)
+          q.cs = 0.0;
+          nd = q;
+        }
       } else {
         sincos((ext ? p1 : p0) * kDeg2Rad, &nd.sn, &nd.cs);
       }
