@@ -830,7 +830,10 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
 #endif
 }
 
-__global__ void __launch_bounds__(kThreads) vfo_rows_kernel(const VfoParams p, const int mode) {
+#ifndef PRHF_ROWS_MINB
+#define PRHF_ROWS_MINB 4                                    // 64 registers: 0.43 -> 0.29 ms per 4096-profile launch (3: 0.33)
+#endif
+__global__ void __launch_bounds__(kThreads, PRHF_ROWS_MINB) vfo_rows_kernel(const VfoParams p, const int mode) {
   extern __shared__ __align__(16) double smem[];
   __shared__ BlockScratch sc;
   // Programmatic dependent launch: the tile kernel may be scheduled as soon as every CTA of this grid has
@@ -2357,7 +2360,9 @@ cudaError_t launch_vfo_tiles_global(const VfoParams& p, int mode, bool literal, 
 }
 
 cudaError_t launch_vfo_rows(const VfoParams& p, int mode, int64_t n_profiles, cudaStream_t stream) {
-  const size_t smem = p.levels_in_global ? 0 : vfo_rows_smem_bytes(p.n_alt);
+  // (the thread-per-frequency mapping needs no per-warp scratch behind the four staged arrays: more CTAs per SM)
+  const size_t smem = p.levels_in_global ? 0
+                      : (p.k1_lane_mode ? sizeof(double) * 4 * (size_t)p.n_alt : vfo_rows_smem_bytes(p.n_alt));
   cudaError_t e = grant_dynamic_smem((const void*)vfo_rows_kernel, 0, smem);
   if (e != cudaSuccess) return e;
   const int rows_per_cta = (p.k1_lane_mode || p.levels_in_global) ? kThreads : kRowsPerCta * p.rows_per_warp;
