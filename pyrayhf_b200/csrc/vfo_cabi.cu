@@ -911,7 +911,9 @@ int prhf_vfo_stream_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64
                                 ((freq_shared || freq_dev) ? 0 : (size_t)n_freq) + (vh_direct ? 0 : (size_t)n_freq)) +
                           ((status && st_dev) ? 0 : sizeof(int));
   if (chunk == 0) {
-    chunk = std::min<int64_t>(4096, std::max<int64_t>(256, (n_profiles + 7) / 8));
+    // (every chunk ends with the tail of a persistent tile kernel, ~40 us of draining SMs, and a launch gap: at most
+    //  about five chunks per call once the opening quarter-chunk hides the first copy-in)
+    chunk = std::min<int64_t>(4096, std::max<int64_t>(256, (n_profiles + 3) / 4));
     if (per_prof == 0) chunk = n_profiles;                    // nothing to stage: one launch sequence
   }
   if (per_prof > 0) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)(((size_t)512 << 20) / per_prof)));
