@@ -137,3 +137,28 @@ def test_queued_mode_defers_rows_whose_window_exceeds_the_node_buffer(mode, monk
     lit, tru = _truth_and_literal(freq, den[sample], bmag[sample], bpsi[sample], alt, mode, n_points)
     for k, q in enumerate(sample):
         assert_parity(a[q], lit[k], tru[k], mode, "deferred rows %s profile %d" % (mode, q))
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+@pytest.mark.parametrize("drift_deg_per_km", [0.01, 0.5])
+def test_espace_loop_with_a_rotating_field_angle(mode, drift_deg_per_km):
+    """Real IGRF fields turn with height.  0.01 deg/km is the second-order rotation path (FastS), 0.5 deg/km the
+    eighth-order one (FastL); both keep the node form (coordinate + slopes) in E-space, unlike the constant-angle path.
+    Single profile (segments) and a 200-profile batch (queue kernel) against the oracle."""
+    import torch
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import synth
+    alt, freq = synth.default_alt(), synth.default_freq()[::4]
+    lat, lon = synth.grid_subset(200)
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    bpsi = bpsi + drift_deg_per_km * (alt - alt[0])[None, :]
+    n_points = 6001
+    got1 = prhf.vertical_forward_operator(freq, den[3], bmag[3], bpsi[3], alt, mode, n_points)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+    got = prhf.vertical_forward_operator_batched(*t, mode, n_points).cpu().numpy()
+    sample = [3, 100, 199]
+    lit, tru = _truth_and_literal(freq, den[sample], bmag[sample], bpsi[sample], alt, mode, n_points)
+    assert_parity(got1, lit[0], tru[0], mode, "rotating angle, single profile %s" % mode)
+    for k, q in enumerate(sample):
+        assert_parity(got[q], lit[k], tru[k], mode, "rotating angle %g deg/km %s profile %d" % (drift_deg_per_km, mode, q))
