@@ -1,19 +1,27 @@
 // Fused vertical-forward-operator kernels for B200 (sm_100a).
 //
-// Two launches per call, no [n_freq x n_points] array ever reaches HBM:
+// One launch (single profile) or two (batches) per call; no [n_freq x n_points] array ever reaches HBM:
 //
-//   vfo_rows_kernel  (K1)  one CTA per (profile, 8 sounding frequencies), one warp per frequency:
+//   vfo_rows_kernel  (K1)  row setup, one warp (small batches) or one thread (large batches) per sounding frequency:
 //       peak truncation, error status, unmagnetised switch, critical curve X or X+Y at the profile
 //       nodes, running max, validity, reflection height, back-off.          lib:371-407
-//       Output: 8 bytes per (profile, frequency) row (h_c - alt0, NaN = no reflection) and a 32-byte
-//       record per profile.  Rows that do not reflect get their NaN here and cost nothing later.
+//       Output: 8 bytes per (profile, frequency) row (h_c - alt0, NaN = row finished) and a 64-byte
+//       record per profile.  Rows that do not reflect get their NaN here and cost nothing later; on large
+//       batches rows clamped to the first level are finished here too and the rest is queued.
 //
-//   vfo_tile_kernel  (K2)  one CTA per tile = (profile, frequency, segment of the stretched grid):
+//   grid points (K2)       one tile = (profile, frequency, segment of the stretched grid):
 //       stages the profile nodes the tile touches (np.interp slopes, sin/cos of the field angle) in
 //       shared memory, then per grid point: h_i, dh_i (lib:413-416), linear interpolation of
 //       den/bmag/bpsi (lib:424-426), X, Y (lib:500-503), Appleton-Hartree mu' (lib:209-254), the
 //       left-Riemann nansum (lib:288), block reduction, ==0 -> NaN, + min(alt) (lib:290-292).
 //       Everything the reference materialises per grid point lives in registers.
+//         vfo_queue_kernel    large batches: 128-thread CTAs, eight per SM, whole-row tiles drawn from K1's queue by ticket
+//         vfo_tile_kernel     one CTA per row / planned segments of small batches / rows the queue kernel deferred
+//         vfo_rowwarp_kernel  n_points <= 4096: one warp per row, nodes staged once per profile
+//         vfo_solo_kernel     one profile: row setup and tile in ONE launch
+//         vfo_tile_global_kernel  profiles with more levels than shared memory holds
+//       Uniform altitude grids run the grid loop in "E-space" (tile_sum_fast_e): the stretched grid is a geometric
+//       sequence, so the loop computes it with one multiplication per point instead of reading a table.
 //
 // PyRayHF/library.py is abbreviated "lib" throughout.
 #include <cuda_runtime.h>
