@@ -504,7 +504,9 @@ static int vfo_enqueue(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_
   // clamped to the first level itself and appends the rows that still need their grid points to a queue; the tile
   // kernel runs one CTA per resident slot and strides over the queue.  Against one CTA per row this drops the launch of
   // a CTA for every row that does not reflect (two of three on a global grid) and keeps every queued row equally long.
-  const bool lane_k1 = !planned && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count;
+  // (not in solo mode: the single-launch kernel scans its one row with the whole block -- 148 ... 222 profiles of ONE
+  //  frequency used to take the thread-per-frequency branch there and left their reflecting rows unwritten)
+  const bool lane_k1 = !planned && !solo && ctx->use_k1_lanes && n_profiles >= (int64_t)ctx->sm_count;
   const bool queued = !solo && !planned && !big && lane_k1 && ctx->queue_mode > 0 && n_seg == 1 &&
                       !(n_points <= prhf::kRowWarpMaxPoints && ctx->use_rowwarp);
   if (queued) {

@@ -162,3 +162,72 @@ def test_espace_loop_with_a_rotating_field_angle(mode, drift_deg_per_km):
     assert_parity(got1, lit[0], tru[0], mode, "rotating angle, single profile %s" % mode)
     for k, q in enumerate(sample):
         assert_parity(got[q], lit[k], tru[k], mode, "rotating angle %g deg/km %s profile %d" % (drift_deg_per_km, mode, q))
+
+
+@pytest.mark.parametrize("n_prof,n_freq,n_points", [(150, 300, 4100), (200, 1, 5000), (148, 33, 8191), (1000, 7, 4097)])
+def test_queued_mode_shapes(n_prof, n_freq, n_points, monkeypatch):
+    """Shapes around the edges of the queued decomposition: more frequencies than the 256 threads of a row-setup CTA
+    (several CTAs per profile append to the queue), a single frequency, exactly 148 profiles, many short profiles'
+    worth of rows; X-mode against the one-CTA-per-row form."""
+    import torch
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import _cabi, synth
+    alt = synth.default_alt()
+    freq = np.linspace(0.3, 16.0, n_freq) if n_freq > 1 else np.array([5.0])
+    lat, lon = synth.grid_subset(n_prof)
+    den, bmag, bpsi = synth.profiles_at(lat, lon, alt)
+    dev = torch.device("cuda:0")
+
+    def run():
+        t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+        return prhf.vertical_forward_operator_batched(*t, "X", n_points).cpu().numpy()
+
+    a = run()
+    monkeypatch.setenv("PRHF_QUEUE", "0")
+    monkeypatch.setattr(_cabi, "_contexts", {})
+    b = run()
+    assert a.shape == (n_prof, n_freq)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = np.isfinite(a)
+    assert m.any() and np.max(np.abs(a[m] - b[m]) / np.abs(b[m])) < 1e-12
+    lit, tru = _truth_and_literal(freq, den[:2], bmag[:2], bpsi[:2], alt, "X", n_points)
+    for q in range(2):
+        assert_parity(a[q], lit[q], tru[q], "X", "shape %dx%dx%d profile %d" % (n_prof, n_freq, n_points, q))
+
+
+def test_every_decomposition_writes_every_row():
+    """Shapes on both sides of every switch between the work decompositions (solo <-> planned <-> one CTA per row <->
+    queued; row-per-warp <-> tile kernels; warp- <-> thread-per-frequency row setup): the output starts as a sentinel,
+    every entry must be overwritten, and sampled rows must equal the single-profile call.  (Found in round 2: 148 ... 222
+    profiles of ONE frequency ran the single-launch kernel with the thread-per-frequency flag set and left their
+    reflecting rows unwritten.)"""
+    import torch
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import synth
+    alt = synth.default_alt()
+    dev = torch.device("cuda:0")
+    lat, lon = synth.grid_subset(512)
+    den_all, bmag_all, bpsi_all = synth.profiles_at(lat, lon, alt)
+    t_alt = torch.from_numpy(alt).to(dev)
+    checked = 0
+    for n_freq in (1, 2, 9, 174, 257):
+        freq = np.linspace(0.5, 14.0, n_freq) if n_freq > 1 else np.array([5.0])
+        t_freq = torch.from_numpy(freq).to(dev)
+        for n_prof in (1, 2, 3, 23, 24, 25, 147, 148, 149, 222, 223, 300, 512):
+            if n_prof * n_freq > 60000:
+                continue
+            t = [torch.from_numpy(np.ascontiguousarray(v[:n_prof])).to(dev) for v in (den_all, bmag_all, bpsi_all)]
+            for n_points in (1, 2, 200, 2047, 2048, 4096, 4097, 5000):
+                out = torch.full((n_prof, n_freq), -7.0, dtype=torch.float64, device=dev)
+                prhf.vertical_forward_operator_batched(t_freq, t[0], t[1], t[2], t_alt, "X", n_points, out=out)
+                a = out.cpu().numpy()
+                label = "P=%d F=%d n=%d" % (n_prof, n_freq, n_points)
+                assert not (a == -7.0).any(), label + ": %d rows never written" % int((a == -7.0).sum())
+                if n_points in (200, 2048, 5000):
+                    q = n_prof - 1
+                    one = prhf.vertical_forward_operator(freq, den_all[q], bmag_all[q], bpsi_all[q], alt, "X", n_points)
+                    assert np.array_equal(np.isnan(one), np.isnan(a[q])), label
+                    m = np.isfinite(one)
+                    assert np.max(np.abs(one[m] - a[q][m]) / np.abs(one[m]), initial=0.0) < 1e-11, label
+                checked += 1
+    assert checked > 300
