@@ -195,7 +195,8 @@ def test_queued_mode_shapes(n_prof, n_freq, n_points, monkeypatch):
         assert_parity(a[q], lit[q], tru[q], "X", "shape %dx%dx%d profile %d" % (n_prof, n_freq, n_points, q))
 
 
-def test_every_decomposition_writes_every_row():
+@pytest.mark.parametrize("mode,grid", [("X", "uniform"), ("O", "uniform"), ("X", "jittered"), ("O", "jittered")])
+def test_every_decomposition_writes_every_row(mode, grid):
     """Shapes on both sides of every switch between the work decompositions (solo <-> planned <-> one CTA per row <->
     queued; row-per-warp <-> tile kernels; warp- <-> thread-per-frequency row setup): the output starts as a sentinel,
     every entry must be overwritten, and sampled rows must equal the single-profile call.  (Found in round 2: 148 ... 222
@@ -205,12 +206,14 @@ def test_every_decomposition_writes_every_row():
     import pyrayhf_b200 as prhf
     from pyrayhf_b200 import synth
     alt = synth.default_alt()
+    if grid == "jittered":                                    # not uniform: the table-reading m-space loop
+        alt = alt + np.random.default_rng(5).uniform(-0.3, 0.3, alt.size)
     dev = torch.device("cuda:0")
     lat, lon = synth.grid_subset(512)
     den_all, bmag_all, bpsi_all = synth.profiles_at(lat, lon, alt)
     t_alt = torch.from_numpy(alt).to(dev)
     checked = 0
-    for n_freq in (1, 2, 9, 174, 257):
+    for n_freq in ((1, 2, 9, 174, 257) if grid == "uniform" else (1, 9, 174)):
         freq = np.linspace(0.5, 14.0, n_freq) if n_freq > 1 else np.array([5.0])
         t_freq = torch.from_numpy(freq).to(dev)
         for n_prof in (1, 2, 3, 23, 24, 25, 147, 148, 149, 222, 223, 300, 512):
@@ -219,15 +222,15 @@ def test_every_decomposition_writes_every_row():
             t = [torch.from_numpy(np.ascontiguousarray(v[:n_prof])).to(dev) for v in (den_all, bmag_all, bpsi_all)]
             for n_points in (1, 2, 200, 2047, 2048, 4096, 4097, 5000):
                 out = torch.full((n_prof, n_freq), -7.0, dtype=torch.float64, device=dev)
-                prhf.vertical_forward_operator_batched(t_freq, t[0], t[1], t[2], t_alt, "X", n_points, out=out)
+                prhf.vertical_forward_operator_batched(t_freq, t[0], t[1], t[2], t_alt, mode, n_points, out=out)
                 a = out.cpu().numpy()
                 label = "P=%d F=%d n=%d" % (n_prof, n_freq, n_points)
                 assert not (a == -7.0).any(), label + ": %d rows never written" % int((a == -7.0).sum())
                 if n_points in (200, 2048, 5000):
                     q = n_prof - 1
-                    one = prhf.vertical_forward_operator(freq, den_all[q], bmag_all[q], bpsi_all[q], alt, "X", n_points)
+                    one = prhf.vertical_forward_operator(freq, den_all[q], bmag_all[q], bpsi_all[q], alt, mode, n_points)
                     assert np.array_equal(np.isnan(one), np.isnan(a[q])), label
                     m = np.isfinite(one)
-                    assert np.max(np.abs(one[m] - a[q][m]) / np.abs(one[m]), initial=0.0) < 1e-11, label
+                    assert np.max(np.abs(one[m] - a[q][m]) / np.abs(one[m]), initial=0.0) < (1e-11 if mode == "X" else 1e-9), label
                 checked += 1
-    assert checked > 300
+    assert checked > 150
