@@ -234,3 +234,34 @@ def test_every_decomposition_writes_every_row(mode, grid):
                     assert np.max(np.abs(one[m] - a[q][m]) / np.abs(one[m]), initial=0.0) < (1e-11 if mode == "X" else 1e-9), label
                 checked += 1
     assert checked > 150
+
+
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_queued_mode_with_per_profile_grids_and_frequencies(mode):
+    """[P, A] altitude grids and [P, F] frequency sets (every profile its own), 300 profiles at 5000 points per row:
+    the queue kernel must index both with the profile's stride.  Against the single-profile call."""
+    import torch
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import synth
+    rng = np.random.default_rng(11)
+    alt0 = synth.default_alt()
+    n_prof, n_freq, n_points = 300, 40, 5000
+    lat, lon = synth.grid_subset(n_prof)
+    shift = rng.uniform(-3.0, 3.0, n_prof)
+    alt = alt0[None, :] + shift[:, None]                      # still uniform per profile, different origin
+    den = np.empty((n_prof, alt0.size)); bmag = np.empty_like(den); bpsi = np.empty_like(den)
+    for q in range(n_prof):
+        d, b, p = synth.profiles_at(lat[q:q + 1], lon[q:q + 1], alt[q])
+        den[q], bmag[q], bpsi[q] = d[0], b[0], p[0]
+    freq = np.sort(rng.uniform(0.5, 14.0, (n_prof, n_freq)), axis=1)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (freq, den, bmag, bpsi, alt)]
+    out = torch.full((n_prof, n_freq), -7.0, dtype=torch.float64, device=dev)
+    prhf.vertical_forward_operator_batched(*t, mode, n_points, out=out)
+    a = out.cpu().numpy()
+    assert not (a == -7.0).any()
+    for q in (0, 1, 149, 150, 299):
+        one = prhf.vertical_forward_operator(freq[q], den[q], bmag[q], bpsi[q], alt[q], mode, n_points)
+        assert np.array_equal(np.isnan(one), np.isnan(a[q])), q
+        m = np.isfinite(one)
+        assert np.max(np.abs(one[m] - a[q][m]) / np.abs(one[m]), initial=0.0) < (1e-11 if mode == "X" else 1e-9), q
