@@ -512,6 +512,11 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
       const double step = fabs(__dsub_rn(s_psi[k + 1], ps)) * kDeg2Rad;
       if (!(step <= kMaxRotateStep)) chk |= 2;
       step_max = fmax(step_max, step);
+      // the quadratic form of the small-rotation path (stage_nodes, E-space) drops (dB/B) (d psi)^2 / 2 per level: it
+      // must stay at the 1e-11 the rotation's own truncation (d psi)^3 / 6 is held to -- next to the reflection level
+      // mu^2 cancels to 1e-8 of its operands and a SYSTEMATIC relative error of the field terms is amplified
+      // accordingly (a bound of 1e-3 on dB/B alone let a random test profile through at 2.2e-9)
+      if (!(fabs(__dsub_rn(s_b[k + 1], b)) * (step * step) <= 2e-11 * fabs(b))) chk |= 16;
     }
   }
   PRHF_TRACE_X(0);
@@ -543,7 +548,7 @@ __device__ __forceinline__ void rows_body(const VfoParams& p, const int mode, co
     ProfileRecord rec;
     rec.nt = nt;
     rec.flags = (iso ? kFlagIso : 0) | (any_general ? kFlagGeneral : 0) | (status ? kFlagFailed : 0) |
-                (step_max == 0.0 ? kFlagPsiConst : 0) | (step_max <= kSmallRotateStep ? kFlagPsiSmall : 0) |
+                (step_max == 0.0 ? kFlagPsiConst : 0) | ((step_max <= kSmallRotateStep && !(r2.flags & 16)) ? kFlagPsiSmall : 0) |
                 (any_nonuniform ? 0 : kFlagUniformAlt) | ((r2.flags & 8) ? kFlagAltUnsorted : 0);
     rec.alt_min = alt_min;
     rec.inv_dalt = (nt > 1) ? (double)(nt - 1) * rcp_fast(s_alt[nt - 1] - alt0) : 0.0;
@@ -1051,6 +1056,10 @@ __device__ __forceinline__ void espace_xy_node(double E, const Node& nd, const R
     *X_out = fma(nd.x, E, nd.alt);
     *yth_out = fma(nd.y, E, nd.sx);
     *yl_out = fma(nd.srad, E, nd.sy);
+  } else if (PATH == kPathFastS) {
+    *X_out = fma(nd.x, E, nd.alt);
+    *yth_out = fma(fma(nd.sy, E, nd.y), E, nd.sx);
+    *yl_out = fma(fma(nd.cs, E, nd.sn), E, nd.srad);
   } else {
     fast_xy_node<PATH, false>(E, nd, rc, X_out, yth_out, yl_out);
   }
@@ -1649,7 +1658,43 @@ __device__ __forceinline__ void stage_nodes(Node* nodes, int k0, int n, int nt, 
           nd = q;
         }
       } else {
-        sincos((ext ? p1 : p0) * kDeg2Rad, &nd.sn, &nd.cs);
+        const bool quadratic = (space == kSpaceE && path == kPathFastS);
+        if (!quadratic) sincos((ext ? p1 : p0) * kDeg2Rad, &nd.sn, &nd.cs);
+        if (quadratic) {
+          // E-space, field angle turning by <= 4e-4 rad per level (every IGRF profile): the two field terms
+          //   YTh = Y sin(psi) / sqrt(2),  YL = Y cos(psi),   Y and psi linear in E within the segment
+          // as QUADRATICS in E, intercept form: two FMAs each instead of the interpolation of Y, the second-order
+          // rotation and the two products (13 -> 5 FP64 instructions per point for the three interpolants).
+          // The Taylor expansion is centred at the UPPER end of the segment -- the next level, or the row's own top
+          // point E = 1 in the segment that holds the reflection level -- because that is where the integrand is
+          // singular: a relative error eps of the field terms at the top of the row moves the virtual height by
+          // ~3000 eps (an expansion about the segment's lower level, 3.5e-12 off at the far end on the tutorial's Night
+          // profile, cost 1e-8).  Dropped: the cubic terms, (dB/B) (d psi)^2 / 2 + (d psi)^3 / 6 relative at the segment's
+          // LOWER end (<= 1e-11 + 1.1e-11 by the limits the row setup enforces for this path), falling off with the cube
+          // of the distance from the centre.  Cancellation of the intercept form: as for the constant-angle path.
+          const double ej = nd.alt;
+          const double e_up = seg && !ext ? (kStretchA - (a1 - rec.alt0) * inv_span) * kStretchDen : ej;
+          const double ec = fmax(e_up, 1.0);
+          const double tc = ec - ej;
+          const double y = fma(nd.sy, tc, nd.y), sy = nd.sy, r = nd.srad;
+          double sk, ck;
+          sincos(fma(r, tc, (ext ? p1 : p0) * kDeg2Rad), &sk, &ck);
+          const double h = 0.70710678118654752;
+          const double a0 = (y * sk) * h, a1c = (fma(sy, sk, (y * ck) * r)) * h;
+          const double a2 = (fma(sy * ck, r, -0.5 * ((y * sk) * (r * r)))) * h;
+          const double b0 = y * ck, b1c = fma(sy, ck, -((y * sk) * r));
+          const double b2 = -fma(sy * sk, r, 0.5 * ((y * ck) * (r * r)));
+          Node q;
+          q.alt = fma(-nd.sx, ej, nd.x);                  // X: intercept, slope
+          q.x = nd.sx;
+          q.sx = fma(fma(a2, ec, -a1c), ec, a0);          // YTh(E) = c0 + c1 E + c2 E^2
+          q.y = fma(-2.0 * a2, ec, a1c);
+          q.sy = a2;
+          q.srad = fma(fma(b2, ec, -b1c), ec, b0);        // YL(E)
+          q.sn = fma(-2.0 * b2, ec, b1c);
+          q.cs = b2;
+          nd = q;
+        }
       }
     } else {
       double sd = 0.0, sb = 0.0, sp = 0.0;
