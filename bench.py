@@ -355,6 +355,17 @@ def next_rows_section(torch, dev, stream, ctx, freq, den, bmag, bpsi, alt, with_
             None, 0, vp(npth.data_ptr()), sp)))
         entry = {"rays": int(f_r.size), "rays_with_a_path": int((npth > 0).sum().item()), "ms": ms,
                  "rays_per_s": f_r.size / (ms * 1e-3)}
+        # the same fan through the fan entry: refractive-index field once per frequency instead of once per ray
+        scal_pairs = scal.clone()
+        t_ff, t_fe = t(freq * 1e6), t(elev)
+        ms_fan = timed(torch, stream, lambda: ctx.check(L.prhf_snell_fan_f64(
+            ctx.handle, vp(t_ff.data_ptr()), freq.size, vp(t_fe.data_ptr()), elev.size, vp(ta.data_ptr()),
+            vp(td.data_ptr()), vp(tb.data_ptr()), vp(tp.data_ptr()), alt.size, 1, geo, 0, 1.0, 200.0, 400, 6371.0,
+            vp(scal.data_ptr()), None, None, 0, vp(npth.data_ptr()), sp)))
+        entry["fan_entry_ms"] = ms_fan
+        entry["fan_entry_rays_per_s"] = f_r.size / (ms_fan * 1e-3)
+        entry["fan_entry_equals_per_ray_entry_bitwise"] = bool(torch.equal(
+            torch.nan_to_num(scal, nan=-1.0), torch.nan_to_num(scal_pairs, nan=-1.0)))
         if with_cpu:
             from oracle import snell_oracle
             idx = np.linspace(0, f_r.size - 1, 12).astype(int)

@@ -217,6 +217,19 @@ int prhf_snell_f64(prhf_ctx* ctx, const double* f0_hz, const double* elevation_d
                    void* cuda_stream);
 
 /*
+ * The same tracers for a whole (frequency x elevation) FAN: ray f * n_elev + e has frequency f0_hz[f] and launch
+ * elevation elevation_deg[e].  The refractive-index field (find_mu_mup at the profile levels, library.py:1181-1185)
+ * depends on the frequency only and is computed once per frequency instead of once per ray; every output is
+ * bit-identical to prhf_snell_f64 called with the n_freq * n_elev (frequency, elevation) pairs written out.
+ *   scalars_out [n_freq * n_elev x 5], x_out / z_out [n_freq * n_elev x path_stride], n_path_out [n_freq * n_elev].
+ */
+int prhf_snell_fan_f64(prhf_ctx* ctx, const double* f0_hz, int n_freq, const double* elevation_deg, int n_elev,
+                       const double* alt_km, const double* ne, const double* babs, const double* bpsi, int n_alt,
+                       int mode, int geometry, unsigned flags, double dz_target_km, double apex_boost, int max_substeps,
+                       double r_e_km, double* scalars_out, double* x_out, double* z_out, int path_stride,
+                       int* n_path_out, void* cuda_stream);
+
+/*
  * Residual of the inversion objective on DEVICE buffers (replaces the arithmetic tail of residual_VH,
  * library.py:660-668, for a batch of candidate profiles): NaN model heights are replaced by
  * max(nanmean|vh_model[p,:]|, 100) (library.py:664-665), residual = vh_obs - vh_model (library.py:668).

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "prhf_selftest_math", "prhf_kernel_timing", "prhf_residual_f64", "prhf_argmin_f64",
     "prhf_den2freq_f64", "prhf_find_x_f64", "prhf_find_y_f64", "prhf_smooth_grid_f64",
     "prhf_regrid_f64", "prhf_find_vh_f64", "prhf_synth_profiles_f64",
-    "prhf_snell_f64",
+    "prhf_snell_f64", "prhf_snell_fan_f64",
 )
 
 _vp = ctypes.c_void_p
@@ -122,6 +122,9 @@ def load():
         L.prhf_snell_f64.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _u, _d, _d, _i, _d,
                                      _vp, _vp, _vp, _i, _vp, _vp]
         L.prhf_snell_f64.restype = _i
+        L.prhf_snell_fan_f64.argtypes = [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _u, _d, _d, _i, _d,
+                                         _vp, _vp, _vp, _i, _vp, _vp]
+        L.prhf_snell_fan_f64.restype = _i
         L.prhf_launch_count.argtypes = [_vp]
         L.prhf_launch_count.restype = _i64
         _lib = L

@@ -63,6 +63,8 @@ struct prhf_ctx {
   int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   int queue_mode = 1;                // PRHF_QUEUE=0: large batches with one tile-kernel CTA per row (no live-row queue)
+  double* snell_field = nullptr;          // per-frequency refractive-index field of prhf_snell_fan_f64
+  size_t snell_field_cap = 0;
   prhf::LiveRow* live_list = nullptr;     // [2 x live_list_cap]: the queue, then the rows deferred to the full-width kernel
   size_t live_list_cap = 0;
   void* node_table = nullptr;        // un-scaled nodes of profiles too long for shared memory (n_alt > prhf_max_n_alt)
@@ -177,6 +179,7 @@ int ensure_plan(prhf_ctx* ctx, size_t n_rows) {
   }
   if (n_rows > ctx->live_list_cap) {
     if (ctx->live_list) cudaFree(ctx->live_list);
+  if (ctx->snell_field) cudaFree(ctx->snell_field);
     ctx->live_list = nullptr;
     ctx->live_list_cap = 0;
     PRHF_CUDA(ctx, cudaMalloc(&ctx->live_list, sizeof(prhf::LiveRow) * 2 * n_rows));
@@ -1329,8 +1332,63 @@ int prhf_snell_f64(prhf_ctx* ctx, const double* f0_hz, const double* elevation_d
   P.z_out = z_out;
   P.path_stride = path_stride;
   P.n_path = n_path_out;
+  P.rays_per_freq = 0;
+  P.field = nullptr;
   PRHF_CUDA(ctx, prhf::launch_snell(P, ctx->max_smem_optin, (cudaStream_t)cuda_stream));
   ctx->launches++;
+  return PRHF_OK;
+}
+
+int prhf_snell_fan_f64(prhf_ctx* ctx, const double* f0_hz, int n_freq, const double* elevation_deg, int n_elev,
+                       const double* alt_km, const double* ne, const double* babs, const double* bpsi, int n_alt,
+                       int mode, int geometry, unsigned flags, double dz_target_km, double apex_boost, int max_substeps,
+                       double r_e_km, double* scalars_out, double* x_out, double* z_out, int path_stride,
+                       int* n_path_out, void* cuda_stream) {
+  if (!ctx || n_freq < 0 || n_elev < 0 || n_alt < 1) return PRHF_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) return PRHF_ERR_BAD_MODE;
+  if (geometry != 0 && geometry != 1) return PRHF_ERR_INVALID_ARG;
+  if (n_freq == 0 || n_elev == 0) return PRHF_OK;
+  if (!f0_hz || !elevation_deg || !alt_km || !ne || !babs || !bpsi || !scalars_out) return PRHF_ERR_INVALID_ARG;
+  if ((x_out == nullptr) != (z_out == nullptr)) return PRHF_ERR_INVALID_ARG;
+  if (x_out && path_stride < 2 * (n_alt + 1) + 1) return PRHF_ERR_INVALID_ARG;
+  if (geometry == 1 && (!(dz_target_km > 0.0) || max_substeps < 1)) return PRHF_ERR_INVALID_ARG;
+  if (prhf::snell_smem_bytes(n_alt) > (size_t)ctx->max_smem_optin) return PRHF_ERR_NALT_TOO_LARGE;
+  DeviceGuard g(ctx->device);
+  // the per-frequency field table lives in the ctx (grown on demand; in-flight launches on the old one must finish)
+  const size_t need = sizeof(double) * 2 * (size_t)(n_alt + 1) * (size_t)n_freq;
+  if (need > ctx->snell_field_cap) {
+    PRHF_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->snell_field) cudaFree(ctx->snell_field);
+    ctx->snell_field = nullptr;
+    ctx->snell_field_cap = 0;
+    PRHF_CUDA(ctx, cudaMalloc(&ctx->snell_field, need));
+    ctx->snell_field_cap = need;
+  }
+  prhf::SnellParams P;
+  P.f0_hz = f0_hz;
+  P.elev_deg = elevation_deg;
+  P.n_rays = (int64_t)n_freq * n_elev;
+  P.alt = alt_km;
+  P.ne = ne;
+  P.babs = babs;
+  P.bpsi = bpsi;
+  P.n_alt = n_alt;
+  P.mode = mode;
+  P.spherical = geometry;
+  P.literal = (flags & PRHF_FLAG_LITERAL) ? 1 : 0;
+  P.dz_target = dz_target_km;
+  P.apex_boost = apex_boost;
+  P.max_substeps = max_substeps;
+  P.r_e = r_e_km;
+  P.scalars = scalars_out;
+  P.x_out = x_out;
+  P.z_out = z_out;
+  P.path_stride = path_stride;
+  P.n_path = n_path_out;
+  P.rays_per_freq = n_elev;
+  P.field = ctx->snell_field;
+  PRHF_CUDA(ctx, prhf::launch_snell(P, ctx->max_smem_optin, (cudaStream_t)cuda_stream));
+  ctx->launches += 2;
   return PRHF_OK;
 }
 

@@ -169,6 +169,11 @@ struct SnellParams {
   double* z_out;
   int path_stride;
   int* n_path;             // optional [n_rays]: points on the path, 0 = no ray (every output NaN)
+  // fan entry (prhf_snell_fan_f64): f0_hz [n_freq], elev_deg [rays_per_freq], ray = f * rays_per_freq + e, and the
+  // refractive-index field computed once per frequency: field [n_freq x 2 x (n_alt + 1)] (mu, then mu').  0 / null: one
+  // (f0, elevation) pair per ray and the field computed by every ray itself.
+  int rays_per_freq;
+  double* field;
 };
 size_t snell_smem_bytes(int n_alt);
 cudaError_t launch_snell(const SnellParams& p, int max_smem_optin, cudaStream_t stream);

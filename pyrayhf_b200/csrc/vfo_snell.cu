@@ -36,25 +36,12 @@ struct WarpRay {
   int* vidx;      // [n]   full-grid index of every compacted level
 };
 
-template <int MODE, bool SPH, bool LITERAL>
-__device__ void trace_one_ray(const SnellParams& p, int64_t ray, const double* s_alt, int n, int ins, WarpRay w) {
-  const int lane = threadIdx.x & 31;
+// Phase A for one sounding frequency: mu and mu' at the n levels (ground level inserted), NaN-masked as lib:1184-1185,
+// written by the lanes of one warp to mu_out[k], mup_out[k].
+template <int MODE, bool LITERAL>
+__device__ __forceinline__ void field_levels(const SnellParams& p, double f0, int n, int ins, int lane, double* mu_out,
+                                             double* mup_out) {
   const unsigned full = 0xffffffffu;
-  const double f0 = p.f0_hz[ray];
-  const double elev = p.elev_deg[ray];
-  double* out = p.scalars + ray * 5;
-  auto fail = [&]() {                                        // the reference returns NaN for every key
-    if (lane < 5) out[lane] = CUDART_NAN;
-    if (lane == 0 && p.n_path) p.n_path[ray] = 0;
-    if (p.x_out) {
-      for (int k = lane; k < p.path_stride; k += 32) {
-        p.x_out[ray * (int64_t)p.path_stride + k] = CUDART_NAN;
-        p.z_out[ray * (int64_t)p.path_stride + k] = CUDART_NAN;
-      }
-    }
-  };
-
-  // ---- A: field ----
   double ymax = -1.0;                                        // nanmax |Y| (lib:201); -1 = no non-NaN value
   for (int k = lane; k < n; k += 32) {
     const int src = max(k - ins, 0);                         // np.interp(0, alt, v) clamps to v[0] (lib:1171-1173)
@@ -77,8 +64,52 @@ __device__ void trace_one_ray(const SnellParams& p, int64_t ray, const double* s
       sincos(p.bpsi[src] * kDeg2Rad, &sn, &cs);
       mup = ah_fast<MODE>(X, y_literal(p.babs[src], f0), sn, cs, &mu);
     }
-    w.xu[k] = (isfinite(mu) && mu > 0.0) ? mu : CUDART_NAN;          // lib:1184
-    w.mup[k] = (isfinite(mup) && mup > 0.0) ? mup : CUDART_NAN;      // lib:1185
+    mu_out[k] = (isfinite(mu) && mu > 0.0) ? mu : CUDART_NAN;          // lib:1184
+    mup_out[k] = (isfinite(mup) && mup > 0.0) ? mup : CUDART_NAN;      // lib:1185
+  }
+}
+
+// Fan entry: the refractive-index field depends on the frequency only, so it is computed ONCE per frequency (one warp
+// each) into field[f][0..n) = mu, field[f][n..2n) = mu' and the rays of the fan read it (snell_kernel, p.field).
+template <int MODE, bool LITERAL>
+__global__ void __launch_bounds__(128) snell_field_kernel(const SnellParams p, int n_freq) {
+  const int ins = (p.alt[0] > 0.0) ? 1 : 0;                             // lib:1169
+  const int n = p.n_alt + ins;
+  const int f = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (f >= n_freq) return;
+  double* dst = p.field + (size_t)f * 2 * (size_t)(p.n_alt + 1);
+  field_levels<MODE, LITERAL>(p, p.f0_hz[f], n, ins, threadIdx.x & 31, dst, dst + (p.n_alt + 1));
+}
+
+template <int MODE, bool SPH, bool LITERAL>
+__device__ void trace_one_ray(const SnellParams& p, int64_t ray, const double* s_alt, int n, int ins, WarpRay w) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  // fan entry: ray = frequency index * rays_per_freq + elevation index
+  const int64_t fi = p.rays_per_freq ? ray / p.rays_per_freq : ray;
+  const double f0 = p.f0_hz[fi];
+  const double elev = p.elev_deg[p.rays_per_freq ? ray - fi * p.rays_per_freq : ray];
+  double* out = p.scalars + ray * 5;
+  auto fail = [&]() {                                        // the reference returns NaN for every key
+    if (lane < 5) out[lane] = CUDART_NAN;
+    if (lane == 0 && p.n_path) p.n_path[ray] = 0;
+    if (p.x_out) {
+      for (int k = lane; k < p.path_stride; k += 32) {
+        p.x_out[ray * (int64_t)p.path_stride + k] = CUDART_NAN;
+        p.z_out[ray * (int64_t)p.path_stride + k] = CUDART_NAN;
+      }
+    }
+  };
+
+  // ---- A: field ----
+  if (p.rays_per_freq) {
+    const double* src = p.field + (size_t)fi * 2 * (size_t)(p.n_alt + 1);
+    for (int k = lane; k < n; k += 32) {
+      w.xu[k] = src[k];
+      w.mup[k] = src[(p.n_alt + 1) + k];
+    }
+  } else {
+    field_levels<MODE, LITERAL>(p, f0, n, ins, lane, w.xu, w.mup);
   }
   __syncwarp();
   const double mu0 = w.xu[0];
@@ -295,6 +326,10 @@ cudaError_t launch_snell_t(const SnellParams& p, int max_smem_optin, cudaStream_
   if (e != cudaSuccess) return e;
   int64_t ctas = (p.n_rays + warps - 1) / warps;
   if (ctas > 148 * 16) ctas = 148 * 16;
+  if (p.rays_per_freq) {
+    const int n_freq = (int)(p.n_rays / p.rays_per_freq);
+    snell_field_kernel<MODE, LITERAL><<<(unsigned)((n_freq + 3) / 4), 128, 0, stream>>>(p, n_freq);
+  }
   kern<<<(unsigned)ctas, warps * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }

@@ -32,6 +32,11 @@ def trace_rays_snells_batched(f0_Hz, elevation_deg, alt_km, Ne, Babs, bpsi, mode
     if geometry not in ('cartesian', 'spherical'):
         raise ValueError("geometry must be 'cartesian' or 'spherical'")
     f0, el = np.broadcast_arrays(np.asarray(f0_Hz, dtype=np.float64), np.asarray(elevation_deg, dtype=np.float64))
+    # A (frequency x elevation) fan -- f0_Hz of shape [F, 1] against elevations of shape [E] or [1, E] -- goes through
+    # the fan entry: the refractive-index field depends on the frequency only and is computed once per frequency there.
+    fan = None
+    if f0.ndim == 2 and f0.shape[0] > 0 and f0.shape[1] > 1 and f0.strides[1] == 0 and el.strides[0] == 0:
+        fan = (np.ascontiguousarray(f0[:, 0]), np.ascontiguousarray(el[0, :]))
     f0 = np.ascontiguousarray(f0).reshape(-1)
     el = np.ascontiguousarray(el).reshape(-1)
     alt, ne, bb, ps = (np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in (alt_km, Ne, Babs, bpsi))
@@ -61,11 +66,14 @@ def trace_rays_snells_batched(f0_Hz, elevation_deg, alt_km, Ne, Babs, bpsi, mode
     zs = torch.empty((n_rays, stride), dtype=torch.float64, device=dev) if return_paths else None
     ptr = lambda t: _vp(t.data_ptr()) if t is not None else None             # noqa: E731
     ctx = _cabi.context(dev.index)
-    ctx.check(ctx.lib.prhf_snell_f64(ctx.handle, ptr(t_f), ptr(t_e), n_rays, ptr(t_a), ptr(t_n), ptr(t_b), ptr(t_p),
-                                     n_alt, code, 1 if geometry == 'spherical' else 0,
-                                     _cabi.FLAG_LITERAL if literal else 0, float(dz_target_km), float(apex_boost),
-                                     int(max_substeps), r_e, ptr(scal), ptr(xs), ptr(zs), stride, ptr(n_path),
-                                     _vp(torch.cuda.current_stream(dev).cuda_stream)))
+    tail = (ptr(t_a), ptr(t_n), ptr(t_b), ptr(t_p), n_alt, code, 1 if geometry == 'spherical' else 0,
+            _cabi.FLAG_LITERAL if literal else 0, float(dz_target_km), float(apex_boost), int(max_substeps), r_e,
+            ptr(scal), ptr(xs), ptr(zs), stride, ptr(n_path), _vp(torch.cuda.current_stream(dev).cuda_stream))
+    if fan is not None:
+        t_ff, t_fe = (torch.from_numpy(v).to(dev) for v in fan)
+        ctx.check(ctx.lib.prhf_snell_fan_f64(ctx.handle, ptr(t_ff), fan[0].size, ptr(t_fe), fan[1].size, *tail))
+    else:
+        ctx.check(ctx.lib.prhf_snell_f64(ctx.handle, ptr(t_f), ptr(t_e), n_rays, *tail))
     s = scal.cpu().numpy()
     out = {"group_path_km": s[:, 0].copy(), "group_delay_sec": s[:, 1].copy(), "x_midpoint": s[:, 2].copy(),
            "z_midpoint": s[:, 3].copy(), "ground_range_km": s[:, 4].copy(), "x_apex_km": s[:, 2].copy(),

@@ -128,3 +128,24 @@ def test_fan_against_oracle_and_errors(sn, g):
     b = sn.trace_rays_snells_batched(f, el, al, ne, bb, ps, 'O', literal=True)
     assert np.array_equal(a['n_path'], b['n_path'])
     assert np.allclose(a['group_path_km'], b['group_path_km'], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "spherical"])
+@pytest.mark.parametrize("mode", ["O", "X"])
+def test_fan_entry_equals_the_per_ray_entry(geometry, mode):
+    """prhf_snell_fan_f64 (field once per frequency) against prhf_snell_f64 on the written-out (frequency, elevation)
+    pairs: every output bit for bit, paths included; the Python wrapper takes the fan entry by itself for inputs of
+    shape [F, 1] x [E]."""
+    import pyrayhf_b200 as prhf
+    from pyrayhf_b200 import synth
+    den, bmag, bpsi, alt = synth.single_day_profile()
+    f = np.linspace(1.0e6, 12.0e6, 23)
+    e = np.linspace(3.0, 89.0, 17)
+    fan = prhf.trace_rays_snells_batched(f[:, None], e[None, :], alt, den, bmag, bpsi, mode, geometry=geometry,
+                                         return_paths=True)
+    pairs = prhf.trace_rays_snells_batched(np.repeat(f, e.size), np.tile(e, f.size), alt, den, bmag, bpsi, mode,
+                                           geometry=geometry, return_paths=True)
+    assert fan["group_path_km"].shape == (f.size * e.size,)
+    assert (fan["n_path"] > 0).sum() > 50
+    for key in pairs:
+        assert np.array_equal(fan[key], pairs[key], equal_nan=True), key
