@@ -104,29 +104,35 @@ __device__ __forceinline__ double regrid_interp(double x, int j, const RegridTab
   }
   return r;
 }
-__global__ void __launch_bounds__(kStageThreads) regrid_write_kernel(const RegridParams p) {
+__global__ void __launch_bounds__(kStageThreads) regrid_write_kernel(const RegridParams p, const int n_alt) {
   extern __shared__ double s_tab[];
-  const int nt = p.rec->nt;
-  if (nt < 1) return;
+  // Launched with programmatic stream serialization behind the row-setup kernel: the table below depends on the
+  // caller's profile only, so it is staged -- for ALL n_alt levels, the truncation index is not known yet -- while the
+  // row setup is still running; what that kernel produces (the truncation index, the reflection heights) is read after
+  // griddepcontrol.wait.  The slope of a level is a function of that level and the next one alone, so the first nt
+  // entries are exactly what staging the truncated profile would give (slope[nt-1] is never used, regrid_interp).
   RegridTable t;
   double* w = s_tab;
   t.alt = w;
-  for (int k = threadIdx.x; k < nt; k += blockDim.x) w[k] = p.alt[k];
-  w += nt;
+  for (int k = threadIdx.x; k < n_alt; k += blockDim.x) w[k] = p.alt[k];
+  w += n_alt;
   const double* src[3] = {p.den, p.bmag, p.bpsi};
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     double* v = w;
-    double* sl = w + nt;
-    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+    double* sl = w + n_alt;
+    for (int k = threadIdx.x; k < n_alt; k += blockDim.x) {
       const double f0 = src[q][k];
       v[k] = f0;
-      if (k + 1 < nt) sl[k] = __ddiv_rn(__dsub_rn(src[q][k + 1], f0), __dsub_rn(p.alt[k + 1], p.alt[k]));
+      if (k + 1 < n_alt) sl[k] = __ddiv_rn(__dsub_rn(src[q][k + 1], f0), __dsub_rn(p.alt[k + 1], p.alt[k]));
     }
     t.val[q] = v;
     t.slope[q] = sl;
-    w += 2 * nt;
+    w += 2 * n_alt;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the row-setup grid has completed (no-op without PDL)
+  const int nt = p.rec->nt;
+  if (nt < 1) return;
   __syncthreads();
   const int r = blockIdx.y;
   const double alt0 = t.alt[0];
@@ -306,8 +312,17 @@ cudaError_t launch_regrid_write(const RegridParams& p, int n_alt, cudaStream_t s
   if (chunks < 1) chunks = 1;
   if (p.n_freq > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)chunks, (unsigned)p.n_freq);
-  regrid_write_kernel<<<grid, kStageThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kStageThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, regrid_write_kernel, p, n_alt);
 }
 
 cudaError_t launch_find_vh(const double* X, const double* Y, const double* psi, const double* dh, int64_t n_rows,
