@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <vector>
+#include <chrono>
 
 #include "../../include/pyrayhf_b200.h"
 #include "vfo_kernels.h"
@@ -63,6 +64,9 @@ struct prhf_ctx {
   int force_nseg = 0;                // PRHF_PLAN_NSEG: planned mode uses exactly this many segments per row
   bool use_k1_lanes = true;          // PRHF_NO_K1_LANES=1: row setup always one warp per frequency
   int queue_mode = 1;                // PRHF_QUEUE=0: large batches with one tile-kernel CTA per row (no live-row queue)
+  bool host_trace = false;                // PRHF_HOST_TRACE=1: wall-clock split of prhf_vfo_host_f64 on stderr
+  double host_trace_us[4] = {0, 0, 0, 0};
+  long host_trace_calls = 0;
   double* snell_field = nullptr;          // per-frequency refractive-index field of prhf_snell_fan_f64
   size_t snell_field_cap = 0;
   prhf::LiveRow* live_list = nullptr;     // [2 x live_list_cap]: the queue, then the rows deferred to the full-width kernel
@@ -333,6 +337,7 @@ int prhf_ctx_create(int device, prhf_ctx** out) {
   if (const char* s = getenv("PRHF_NO_ROWWARP")) ctx->use_rowwarp = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_NO_K1_LANES")) ctx->use_k1_lanes = (atoi(s) == 0);
   if (const char* s = getenv("PRHF_QUEUE")) ctx->queue_mode = atoi(s);
+  if (const char* s = getenv("PRHF_HOST_TRACE")) ctx->host_trace = (atoi(s) != 0);
   if (const char* s = getenv("PRHF_PLAN_NSEG")) ctx->force_nseg = atoi(s);
   if (const char* s = getenv("PRHF_SEG_LEN")) ctx->seg_len_override = atoi(s);
   if (const char* s = getenv("PRHF_TARGET_TILES")) ctx->target_tiles = atoll(s);
@@ -783,6 +788,8 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
       off += d8 * count * (size_t)rows;
       return at;
     };
+    const bool host_trace = ctx->host_trace;
+    const auto t0 = std::chrono::steady_clock::now();
     const size_t o_freq = freq_shared ? put(freq_mhz, 0, (size_t)n_freq, 1)
                                       : put(freq_mhz + p0 * freq_profile_stride, freq_profile_stride, (size_t)n_freq, np);
     const size_t o_alt = alt_shared ? put(alt, 0, (size_t)n_alt, 1)
@@ -790,6 +797,7 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     const size_t o_den = put(den + p0 * n_alt, n_alt, (size_t)n_alt, np);
     const size_t o_b = put(bmag + p0 * n_alt, n_alt, (size_t)n_alt, np);
     const size_t o_psi = put(bpsi + p0 * n_alt, n_alt, (size_t)n_alt, np);
+    const auto t1 = std::chrono::steady_clock::now();
     char* out_base = small ? ctx->h_arena : ctx->d_arena;       // pinned host memory is device-addressable (UVA)
     double* d_vh = (double*)(out_base + out_off);
     int* d_st = (int*)(out_base + out_off + d8 * (size_t)n_freq * np);
@@ -817,6 +825,8 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
           if (ge.exec[k]) { cudaGraphExecDestroy(ge.exec[k]); ge.exec[k] = nullptr; }
         ge.calls = 0;
       }
+      // (one executable per call shape: alternating two of them does not shorten cudaGraphLaunch in back-to-back calls,
+      //  profiles/host_trace_r02.txt)
       const int parity = 0;
       if (ge.calls >= 1) {
         if (!ge.exec[parity]) {
@@ -859,9 +869,27 @@ int prhf_vfo_host_f64(prhf_ctx* ctx, const double* freq_mhz, int n_freq, int64_t
     if (!small)
       PRHF_CUDA(ctx, cudaMemcpyAsync(ctx->h_arena + out_off, ctx->d_arena + out_off, out_bytes, cudaMemcpyDeviceToHost,
                                      ctx->stream));
+    const auto t2 = std::chrono::steady_clock::now();
     PRHF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const auto t3 = std::chrono::steady_clock::now();
     memcpy(vh_out + p0 * n_freq, ctx->h_arena + out_off, d8 * (size_t)n_freq * np);
     if (status) memcpy(status + p0, ctx->h_arena + out_off + d8 * (size_t)n_freq * np, sizeof(int) * (size_t)np);
+    if (host_trace) {                                         // PRHF_HOST_TRACE=1: where a host-entry call spends its time
+      const auto t4 = std::chrono::steady_clock::now();
+      auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+      };
+      ctx->host_trace_us[0] += us(t0, t1);
+      ctx->host_trace_us[1] += us(t1, t2);
+      ctx->host_trace_us[2] += us(t2, t3);
+      ctx->host_trace_us[3] += us(t3, t4);
+      if (++ctx->host_trace_calls % 64 == 0) {
+        const double n = 64.0;
+        fprintf(stderr, "prhf host trace (mean of 64 calls, us): pack %.2f  enqueue %.2f  wait %.2f  unpack %.2f\n",
+                ctx->host_trace_us[0] / n, ctx->host_trace_us[1] / n, ctx->host_trace_us[2] / n, ctx->host_trace_us[3] / n);
+        for (double& v : ctx->host_trace_us) v = 0.0;
+      }
+    }
   }
   ctx->have_last_stream = false;                              // everything on this ctx has drained
   return PRHF_OK;
